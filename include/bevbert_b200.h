@@ -1,0 +1,154 @@
+/* bevbert_b200 C ABI — the sm_100a kernels behind the BEVBert hybrid-map encoder hot path.
+ *
+ * Conventions:
+ *   - every pointer is a DEVICE pointer on the current CUDA device unless the name ends in _host;
+ *   - the caller owns every buffer (inputs, outputs, workspaces); nothing here allocates device memory;
+ *   - every launch goes on the caller's `stream` (a cudaStream_t passed as void*); no internal sync;
+ *   - return value: 0 = ok, <0 = error; bb_last_error() returns a thread-local message;
+ *   - re-entrant; one process per GPU.
+ *
+ * The reference (MarSaKi/VLN-BEVBert) has no FFI layer of its own: each entry point cites the PyTorch
+ * call sites in the reference that it replaces (paths relative to the reference root).
+ */
+#ifndef BEVBERT_B200_H
+#define BEVBERT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* bb_last_error(void);
+int bb_abi_version(void);
+/* number of kernels launched through this library by the calling process since load / last reset */
+int64_t bb_launch_count(void);
+void bb_reset_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Batched bf16 GEMM on tcgen05 tensor cores, TMA-fed, fp32 accumulation in TMEM.
+ *   D[b] = epi( alpha * A[b] (M x K) * B[b]^T (N x K) )
+ * Operand element (m,k) of A lives at  A + b1*a_s1 + b2*a_s2 + (a_mn ? k*lda + m : m*lda + k),
+ * operand element (n,k) of B lives at  B + b1*b_s1 + b2*b_s2 + (b_mn ? k*ldb + n : n*ldb + k).
+ * All strides are in elements; lda, ldb and the batch strides must be multiples of 8 (16-byte TMA strides).
+ * Replaces: every nn.Linear / torch.matmul on the path (pretrain_src/model/vilmodel.py:92-94,108-110,
+ * 117,133,146,171,185,314-316,335,348; transformer.py:138-141; pretrain_cmt.py:38-41) and their autograd
+ * backward GEMMs.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct bb_gemm_args {
+  const void* A; /* bf16 */
+  const void* B; /* bf16 */
+  void* D;       /* bf16 or f32 */
+  int32_t M, N, K;
+  int32_t nb1, nb2; /* batch grid; batch index b = (b1, b2) */
+  int32_t a_mn;     /* 0: A is K-major (row-major M x K); 1: A is MN-major (stored K x M) */
+  int32_t b_mn;     /* 0: B is K-major (row-major N x K); 1: B is MN-major (stored K x N) */
+  int64_t lda, a_s1, a_s2;
+  int64_t ldb, b_s1, b_s2;
+  int64_t ldd, d_s1, d_s2; /* output row stride and batch strides (elements of the output dtype) */
+  int32_t out_f32;         /* 0: bf16 output, 1: fp32 output */
+  int32_t accumulate;      /* 1: D += result with fp32 atomics (needs out_f32); implied by split_k>1 */
+  int32_t split_k;         /* >=1; >1 splits K across CTAs (D must be zeroed / hold the addend) */
+  float alpha;
+  const float* bias; /* [N] or NULL; added before the activation */
+  int32_t act;       /* 0 none, 1 exact-erf GELU, 2 ReLU */
+  void* aux_out;     /* bf16, same strides as D: pre-activation (alpha*acc+bias) or NULL */
+  const void* aux_in; /* bf16, same strides as D, or NULL */
+  int32_t epi_mul;   /* 0 none; 1: result *= gelu'(aux_in); 2: result *= (aux_in > 0) */
+  const void* add_in; /* bf16, same strides as D, or NULL: result += add_in (after act/epi_mul) */
+  int32_t block_n;   /* 0 = pick automatically; else N tile (multiple of 16, of 64 when b_mn) */
+} bb_gemm_args;
+
+int bb_gemm_bf16(const bb_gemm_args* args, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * BEV lifting (pretrain_src/model/pretrain_cmt.py:114-137 + bev_utils.py:349-378, 381-406).
+ * depths: f32 (B, V, Hf, Wf) stored units (x depth_scale inside, reference uses x10);
+ * T_c2w f32 (B, V, 4, 4); S_w2c f32 (B, 3); T_w2c f32 (B, 4, 4).
+ * cell_idx: int32 (B, V*Hf*Wf): D*z+x of the BEV cell, or -1 when the point is dropped
+ *           (no depth / outside the map / above the z clip).  Integer path is bit-exact with the oracle.
+ * pc_out: optional f32 (B, V*Hf*Wf, 3) ego-frame point cloud (for tests), may be NULL.
+ * ------------------------------------------------------------------------------------------- */
+int bb_bev_lift_index(const float* depths, const float* T_c2w, const float* S_w2c, const float* T_w2c, int B, int V,
+                      int Hf, int Wf, float depth_scale, float fx, float fy, float cx, float cy, int map_dim,
+                      float map_res, float y_clip, int32_t* cell_idx, float* pc_out, void* stream);
+
+/* Scatter-mean pool of point features into BEV cells (torch_scatter.scatter_mean call sites
+ * bev_utils.py:407-410): feats f32 (B, P, C) -> bev f32 (B, D*D, C) and/or bev_bf16; deterministic
+ * (points of a cell are summed in ascending point order). ob_mask u8 (B, D*D) = !(max==0 && min==0)
+ * (bev_utils.py:412). counts int32 (B, D*D). Any of bev_f32 / bev_bf16 / ob_mask / counts may be NULL. */
+int bb_bev_scatter_mean_f32(const float* feats, const int32_t* cell_idx, int B, int P, int C, int ncell,
+                            float* bev_f32, void* bev_bf16, uint8_t* ob_mask, int32_t* counts, void* stream);
+/* Same for the float64 semantic one-hots (bev_utils.py:417-423): mean, then sem>0 -> 1,
+ * sem_mask u8 (B, D*D) = (sum over classes > 0). */
+int bb_bev_scatter_sem_f64(const double* sems, const int32_t* cell_idx, int B, int P, int S, int ncell,
+                           double* bev_sem, uint8_t* sem_mask, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Row kernels (coalesced, vectorised, warp reductions; fp32 math, bf16 storage).
+ * ------------------------------------------------------------------------------------------- */
+/* f32 -> bf16 cast with optional inverted dropout (nn.Dropout on inputs, pretrain_cmt.py:102-106).
+ * drop_thresh = p * 2^32 (0 = no dropout); scale = 1/(1-p). Element index is the RNG counter. */
+int bb_cast_f32_bf16(const float* src, void* dst, int64_t n, uint64_t seed, uint32_t drop_thresh, float scale,
+                     void* stream);
+int bb_cast_bf16_f32(const void* src, float* dst, int64_t n, void* stream);
+
+/* y = LayerNorm( dropout(x) + residual ) * gamma + beta, optional output dropout
+ * (BertSelfOutput / BertOutput vilmodel.py:150-154,189-193; BertEmbeddings :75-76; nn.LayerNorm sites).
+ * x bf16 or f32 (rows, H); residual bf16 or NULL; y bf16; y_f32 optional f32 copy; mean/rstd f32 (rows)
+ * saved for backward. H % 8 == 0, H <= 4096. */
+int bb_layernorm_fwd(const void* x, int x_f32, const void* residual, const float* gamma, const float* beta,
+                     float eps, int64_t rows, int H, uint64_t seed_in, uint32_t thresh_in, float scale_in,
+                     uint64_t seed_out, uint32_t thresh_out, float scale_out, void* y, float* y_f32, float* mean,
+                     float* rstd, void* stream);
+/* Backward of the above. dy bf16 (or f32 when dy_f32); recomputes z = dropout(x)+residual.
+ * Outputs: dx (bf16, grad wrt x, dropout mask applied) or NULL; dres (bf16, grad wrt residual) or NULL;
+ * dgamma/dbeta f32 [H] are ACCUMULATED into (atomics) — caller zeroes them. */
+int bb_layernorm_bwd(const void* dy, int dy_f32, const void* x, int x_f32, const void* residual, const float* gamma,
+                     const float* mean, const float* rstd, int64_t rows, int H, uint64_t seed_in, uint32_t thresh_in,
+                     float scale_in, uint64_t seed_out, uint32_t thresh_out, float scale_out, void* dx, int dx_f32,
+                     void* dres, float* dgamma, float* dbeta, void* stream);
+
+/* Column sums of a bf16 (rows, N) matrix accumulated into f32 out[N] (bias gradients). */
+int bb_colsum_bf16(const void* x, int64_t rows, int N, int64_t ld, float* out, void* stream);
+
+/* Masked softmax over the last dim (vilmodel.py:117-127, 335-346; transformer.py MHA):
+ * scores f32 (nbatch, H, nq, ld) already scaled; kmask f32 (nbatch, nk) additive (0 / -10000 / -inf) or NULL;
+ * bias f32 (nbatch, nq, nk) additive, shared by heads (graph_sprels, vilmodel.py:391-392) or NULL.
+ * probs bf16 (same layout); probs_drop bf16 = dropout(probs) when thresh != 0 (else may be NULL).
+ * Columns [nk, ld) of the outputs are written as zeros. */
+int bb_softmax_fwd(const float* scores, const float* kmask, const float* bias, int nbatch, int H, int nq, int nk,
+                   int ld, uint64_t seed, uint32_t thresh, float scale, void* probs, void* probs_drop, void* stream);
+/* dS = P * (dPd*keep*scale - sum_k(P * dPd*keep*scale)) * out_scale ; dP f32 (.., ld) wrt dropped probs;
+ * ds bf16; optional dbias f32 (nbatch, nq, nk) += sum over heads (atomics, caller zeroes). */
+int bb_softmax_bwd(const void* probs, const float* dprobs, int nbatch, int H, int nq, int nk, int ld, uint64_t seed,
+                   uint32_t thresh, float scale, float out_scale, void* ds, float* dbias, void* stream);
+
+/* Text embeddings: out f32 (ntok, H) = word[ids] + pos[tok % L] + type[0] (vilmodel.py:62-74; the LayerNorm
+ * that follows is bb_layernorm_fwd with x_f32=1). Backward scatters dz f32 (ntok, H) into the three
+ * embedding-table gradients with f32 atomics; rows with id == padding_idx get no word gradient
+ * (nn.Embedding(padding_idx=0), vilmodel.py:53). Any of dword/dpos/dtype0 may be NULL. */
+int bb_embed_sum(const int64_t* ids, const float* word, const float* pos, const float* type0, int64_t ntok, int L,
+                 int H, float* out, void* stream);
+int bb_embed_scatter_grad(const int64_t* ids, const float* dz, int64_t ntok, int L, int H, int64_t padding_idx,
+                          float* dword, float* dpos, float* dtype0, void* stream);
+
+/* out[r, :] = in[idx[r], :] (bf16 rows of width H); idx < 0 writes zeros. And the adjoint
+ * out[idx[r], :] += in[r, :] in f32. */
+int bb_gather_rows_bf16(const void* in, const int64_t* idx, int64_t nout, int H, void* out, void* stream);
+int bb_scatter_add_rows(const void* in_bf16, const int64_t* idx, int64_t nin, int H, float* out_f32, void* stream);
+
+/* Generic small elementwise helpers on bf16 tensors. */
+int bb_add_bf16(const void* a, const void* b, void* out, int64_t n, void* stream);       /* out = a + b */
+int bb_axpy_f32_from_bf16(const void* x, float* y, int64_t n, void* stream);             /* y += x */
+
+/* Fused softmax cross-entropy over logits f32 (rows, ld) with V valid columns (pretrain_cmt.py:259):
+ * loss[r] = logsumexp - logit[label]; dlogits (bf16, same ld) = (softmax - onehot) * gscale[r] (may be NULL).
+ * label < 0 -> loss 0, zero gradient. */
+int bb_softmax_xent(const float* logits, const int64_t* labels, int64_t rows, int V, int64_t ld, float* loss,
+                    const float* gscale, void* dlogits, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BEVBERT_B200_H */

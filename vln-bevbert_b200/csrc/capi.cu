@@ -1,0 +1,31 @@
+// Error reporting and launch accounting for the C ABI (include/bevbert_b200.h).
+#include <atomic>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/bevbert_b200.h"
+#include "common.h"
+
+namespace bb {
+static thread_local char g_err[512] = "";
+static std::atomic<int64_t> g_launches{0};
+
+int set_error(const char* msg) {
+  strncpy(g_err, msg, sizeof(g_err) - 1);
+  g_err[sizeof(g_err) - 1] = 0;
+  return -1;
+}
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) return 0;
+  char buf[400];
+  snprintf(buf, sizeof(buf), "%s: %s", what, cudaGetErrorString(e));
+  return set_error(buf);
+}
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+}  // namespace bb
+
+extern "C" const char* bb_last_error(void) { return bb::g_err; }
+extern "C" int bb_abi_version(void) { return 1; }
+extern "C" int64_t bb_launch_count(void) { return bb::g_launches.load(); }
+extern "C" void bb_reset_launch_count(void) { bb::g_launches.store(0); }

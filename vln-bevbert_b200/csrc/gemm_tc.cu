@@ -1,0 +1,474 @@
+// Batched bf16 GEMM for sm_100a: TMA -> 128B-swizzled shared memory -> tcgen05.mma (fp32 accumulators
+// in TMEM, double buffered) -> tcgen05.ld epilogue with fused bias / GELU / ReLU / gelu' / residual.
+//
+// Persistent, warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane),
+// warps 2..5 = epilogue (warp w owns TMEM lanes 32*(w%4) .. +31). One CTA per SM.
+//
+// Tile: 128 (M) x block_n (N, runtime, <=256) x 64 (K) per pipeline stage. Operands may be K-major or
+// MN-major (transposed in memory), which gives all of  X*W^T (forward), dY*W (dX) and dY^T*X (dW)
+// and the batched attention products without any transposition pass over HBM.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <mutex>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/bevbert_b200.h"
+#include "common.h"
+#include "ptx.cuh"
+
+namespace bb {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;
+constexpr int UMMA_K = 16;
+constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
+constexpr int NUM_THREADS = 192;
+constexpr int MAX_STAGES = 8;
+constexpr int TMEM_COLS = 512;
+
+struct GemmKParams {
+  int M, N, K;
+  int nb1, nb2;
+  int block_n;
+  int a_mn, b_mn;
+  int split_k, kb_total, kb_per_split;
+  int m_tiles, n_tiles;
+  int stages;
+  int out_f32, atomic;
+  int vec_ok;
+  long long ldd, d_s1, d_s2;
+  void* D;
+  float alpha;
+  const float* bias;
+  int act;
+  __nv_bfloat16* aux_out;
+  const __nv_bfloat16* aux_in;
+  int epi_mul;
+  const __nv_bfloat16* add_in;
+};
+
+struct TileCoord {
+  int split, b1, b2, m_tile, n_tile;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const GemmKParams& p, int tile) {
+  TileCoord t;
+  t.n_tile = tile % p.n_tiles;
+  tile /= p.n_tiles;
+  t.m_tile = tile % p.m_tiles;
+  tile /= p.m_tiles;
+  t.b1 = tile % p.nb1;
+  tile /= p.nb1;
+  t.b2 = tile % p.nb2;
+  tile /= p.nb2;
+  t.split = tile;
+  return t;
+}
+
+__device__ __forceinline__ float bf2f(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+               const GemmKParams p, int total_tiles) {
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte alignment for SWIZZLE_128B atoms
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int b_stage_bytes = p.block_n * BLOCK_K * 2;
+  const int stage_bytes = A_STAGE_BYTES + b_stage_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.stages * stage_bytes);
+  uint64_t* empty_bar = full_bar + MAX_STAGES;
+  uint64_t* tmem_full = empty_bar + MAX_STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < p.stages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_ptr_smem, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(p, tile);
+        const int kb0 = t.split * p.kb_per_split;
+        const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        const int m0 = t.m_tile * BLOCK_M;
+        const int n0 = t.n_tile * p.block_n;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * stage_bytes;
+          uint8_t* sb = sa + A_STAGE_BYTES;
+          mbar_expect_tx(&full_bar[stage], stage_bytes);
+          const int k0 = kb * BLOCK_K;
+          if (!p.a_mn) {
+            tma_load_4d(sa, &tmap_a, &full_bar[stage], k0, m0, t.b1, t.b2);
+          } else {
+            tma_load_4d(sa, &tmap_a, &full_bar[stage], m0, k0, t.b1, t.b2);
+            tma_load_4d(sa + 8192, &tmap_a, &full_bar[stage], m0 + 64, k0, t.b1, t.b2);
+          }
+          if (!p.b_mn) {
+            tma_load_4d(sb, &tmap_b, &full_bar[stage], k0, n0, t.b1, t.b2);
+          } else {
+            for (int j = 0; j < p.block_n / 64; ++j)
+              tma_load_4d(sb + j * 8192, &tmap_b, &full_bar[stage], n0 + 64 * j, k0, t.b1, t.b2);
+          }
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(BLOCK_M, p.block_n, p.a_mn, p.b_mn);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(p, tile);
+        const int kb0 = t.split * p.kb_per_split;
+        const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * 256;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * stage_bytes);
+          const uint32_t sb = sa + A_STAGE_BYTES;
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint64_t da = p.a_mn ? umma_smem_desc(sa + k * 2048, 8192, 1024)
+                                       : umma_smem_desc(sa + k * 32, 16, 1024);
+            const uint64_t db = p.b_mn ? umma_smem_desc(sb + k * 2048, 8192, 1024)
+                                       : umma_smem_desc(sb + k * 32, 16, 1024);
+            umma_bf16_ss(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (4 warps)
+    const int quarter = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile(p, tile);
+      const int row = t.m_tile * BLOCK_M + quarter * 32 + lane;
+      const int n0 = t.n_tile * p.block_n;
+      const bool row_ok = row < p.M;
+      const long long row_off = (long long)t.b1 * p.d_s1 + (long long)t.b2 * p.d_s2 + (long long)row * p.ldd;
+      const bool add_bias = p.bias != nullptr && t.split == 0;
+
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + acc * 256;
+      for (int c = 0; c < p.block_n; c += 16) {
+        const int col0 = n0 + c;
+        if (col0 >= p.N) break;  // warp-uniform
+        uint32_t r[16];
+        tmem_ld16(taddr + c, r);
+        tmem_ld_wait();
+        if (!row_ok) continue;
+        float v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) * p.alpha;
+        const bool full = (col0 + 16 <= p.N);
+        if (add_bias) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (full || col0 + i < p.N) v[i] += __ldg(p.bias + col0 + i);
+        }
+        const long long off = row_off + col0;
+        if (p.aux_out != nullptr) {
+          if (full && p.vec_ok) {
+            __align__(16) __nv_bfloat162 h[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+            uint4* dst = reinterpret_cast<uint4*>(p.aux_out + off);
+            dst[0] = reinterpret_cast<uint4*>(h)[0];
+            dst[1] = reinterpret_cast<uint4*>(h)[1];
+          } else {
+            for (int i = 0; i < 16; ++i)
+              if (col0 + i < p.N) p.aux_out[off + i] = __float2bfloat16(v[i]);
+          }
+        }
+        if (p.act == 1) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = gelu_erf(v[i]);
+        } else if (p.act == 2) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.0f);
+        }
+        if (p.epi_mul != 0) {
+          float a[16];
+          if (full && p.vec_ok) {
+            __align__(16) __nv_bfloat16 h[16];
+            const uint4* src = reinterpret_cast<const uint4*>(p.aux_in + off);
+            reinterpret_cast<uint4*>(h)[0] = __ldg(src);
+            reinterpret_cast<uint4*>(h)[1] = __ldg(src + 1);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) a[i] = bf2f(h[i]);
+          } else {
+            for (int i = 0; i < 16; ++i) a[i] = (col0 + i < p.N) ? bf2f(p.aux_in[off + i]) : 0.0f;
+          }
+          if (p.epi_mul == 1) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] *= dgelu_erf(a[i]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = a[i] > 0.0f ? v[i] : 0.0f;
+          }
+        }
+        if (p.add_in != nullptr) {
+          if (full && p.vec_ok) {
+            __align__(16) __nv_bfloat16 h[16];
+            const uint4* src = reinterpret_cast<const uint4*>(p.add_in + off);
+            reinterpret_cast<uint4*>(h)[0] = __ldg(src);
+            reinterpret_cast<uint4*>(h)[1] = __ldg(src + 1);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] += bf2f(h[i]);
+          } else {
+            for (int i = 0; i < 16; ++i)
+              if (col0 + i < p.N) v[i] += bf2f(p.add_in[off + i]);
+          }
+        }
+        if (p.out_f32) {
+          float* D = reinterpret_cast<float*>(p.D) + off;
+          if (p.atomic) {
+            for (int i = 0; i < 16; ++i)
+              if (full || col0 + i < p.N) atomicAdd(D + i, v[i]);
+          } else if (full && p.vec_ok) {
+            float4* dst = reinterpret_cast<float4*>(D);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          } else {
+            for (int i = 0; i < 16; ++i)
+              if (col0 + i < p.N) D[i] = v[i];
+          }
+        } else {
+          __nv_bfloat16* D = reinterpret_cast<__nv_bfloat16*>(p.D) + off;
+          if (full && p.vec_ok) {
+            __align__(16) __nv_bfloat162 h[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+            uint4* dst = reinterpret_cast<uint4*>(D);
+            dst[0] = reinterpret_cast<uint4*>(h)[0];
+            dst[1] = reinterpret_cast<uint4*>(h)[1];
+          } else {
+            for (int i = 0; i < 16; ++i)
+              if (col0 + i < p.N) D[i] = __float2bfloat16(v[i]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------ host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  });
+  return fn;
+}
+
+// 4-D bf16 tensor map: dims (inner, rows, b1, b2) with element strides (1, ld, s1, s2); box (64, box_rows, 1, 1).
+static int make_map(CUtensorMap* map, const void* base, uint64_t inner, uint64_t rows, uint64_t nb1, uint64_t nb2,
+                    int64_t ld, int64_t s1, int64_t s2, uint32_t box_rows) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return set_error("cuTensorMapEncodeTiled entry point not available");
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return set_error("gemm operand base not 16-byte aligned");
+  if (ld % 8 != 0) return set_error("gemm operand leading dimension must be a multiple of 8 elements");
+  // unused batch dims get a harmless 16-byte-multiple stride
+  if (nb1 <= 1) s1 = ld * (int64_t)rows;
+  if (nb2 <= 1) s2 = s1 * (int64_t)(nb1 > 0 ? nb1 : 1);
+  if (s1 % 8 != 0 || s2 % 8 != 0) return set_error("gemm operand batch strides must be multiples of 8 elements");
+  if (s1 == 0) s1 = 8;
+  if (s2 == 0) s2 = 8;
+  cuuint64_t dims[4] = {inner, rows, nb1 ? nb1 : 1, nb2 ? nb2 : 1};
+  cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)s1 * 2, (cuuint64_t)s2 * 2};
+  cuuint32_t box[4] = {64, box_rows, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[256];
+    snprintf(buf, sizeof(buf),
+             "cuTensorMapEncodeTiled failed (%d): dims=(%llu,%llu,%llu,%llu) ld=%lld s1=%lld s2=%lld box_rows=%u",
+             (int)r, (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2],
+             (unsigned long long)dims[3], (long long)ld, (long long)s1, (long long)s2, box_rows);
+    return set_error(buf);
+  }
+  return 0;
+}
+
+static int g_num_sms = 0;
+static int g_smem_optin = 0;
+
+static int init_device_info() {
+  if (g_num_sms) return 0;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return set_error("cudaGetDevice failed");
+  cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaDeviceGetAttribute(&g_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  if (cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin) != cudaSuccess)
+    return set_error("cudaFuncSetAttribute(max dynamic smem) failed for gemm_tc_kernel");
+  return 0;
+}
+
+}  // namespace bb
+
+extern "C" int bb_gemm_bf16(const bb_gemm_args* a, void* stream_) {
+  using namespace bb;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!a || !a->A || !a->B || !a->D) return set_error("bb_gemm_bf16: null argument");
+  if (a->M <= 0 || a->N <= 0 || a->K <= 0) return set_error("bb_gemm_bf16: M, N, K must be positive");
+  if (int e = init_device_info()) return e;
+  const int nb1 = a->nb1 > 0 ? a->nb1 : 1, nb2 = a->nb2 > 0 ? a->nb2 : 1;
+  const int split_k_req = a->split_k > 1 ? a->split_k : 1;
+  const bool atomic = a->accumulate || split_k_req > 1;
+  if (atomic && !a->out_f32) return set_error("bb_gemm_bf16: accumulate / split_k need fp32 output");
+  if (atomic && (a->act || a->epi_mul || a->aux_out || a->add_in))
+    return set_error("bb_gemm_bf16: accumulate / split_k cannot be combined with a non-linear epilogue");
+
+  GemmKParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = a->M;
+  p.N = a->N;
+  p.K = a->K;
+  p.nb1 = nb1;
+  p.nb2 = nb2;
+  p.a_mn = a->a_mn ? 1 : 0;
+  p.b_mn = a->b_mn ? 1 : 0;
+  p.m_tiles = (a->M + BLOCK_M - 1) / BLOCK_M;
+  // N tile
+  int bn = a->block_n;
+  if (bn <= 0) {
+    const int gran = p.b_mn ? 64 : 16;
+    if (a->N <= 256) {
+      bn = ((a->N + gran - 1) / gran) * gran;  // one N tile
+    } else {
+      // 256-wide tiles when they still give every SM >= 2 tiles; otherwise 128 for load balance
+      const long long t256 = (long long)p.m_tiles * ((a->N + 255) / 256) * nb1 * nb2 * split_k_req;
+      bn = (t256 >= 2LL * g_num_sms) ? 256 : 128;
+    }
+  }
+  if (bn < 16 || bn > 256 || bn % 16 != 0 || (p.b_mn && bn % 64 != 0))
+    return set_error("bb_gemm_bf16: invalid block_n");
+  p.block_n = bn;
+  p.n_tiles = (a->N + bn - 1) / bn;
+  p.kb_total = (a->K + BLOCK_K - 1) / BLOCK_K;
+  int sk = split_k_req < p.kb_total ? split_k_req : p.kb_total;
+  p.kb_per_split = (p.kb_total + sk - 1) / sk;
+  sk = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
+  p.split_k = sk;
+  p.out_f32 = a->out_f32 ? 1 : 0;
+  p.atomic = atomic ? 1 : 0;
+  p.ldd = a->ldd;
+  p.d_s1 = a->d_s1;
+  p.d_s2 = a->d_s2;
+  p.D = a->D;
+  p.alpha = a->alpha;
+  p.bias = a->bias;
+  p.act = a->act;
+  p.aux_out = reinterpret_cast<__nv_bfloat16*>(a->aux_out);
+  p.aux_in = reinterpret_cast<const __nv_bfloat16*>(a->aux_in);
+  p.epi_mul = a->epi_mul;
+  p.add_in = reinterpret_cast<const __nv_bfloat16*>(a->add_in);
+  if (p.epi_mul && !p.aux_in) return set_error("bb_gemm_bf16: epi_mul needs aux_in");
+  // vector epilogue only when every row segment of 16 outputs is 16-byte aligned (for bf16: 8 elements)
+  {
+    const int al = 8;  // elements; covers bf16 (16 B) and f32 (32 B)
+    bool ok = (a->ldd % al == 0) && (a->d_s1 % al == 0) && (a->d_s2 % al == 0);
+    ok = ok && ((reinterpret_cast<uintptr_t>(a->D) & 15) == 0);
+    if (a->aux_out) ok = ok && ((reinterpret_cast<uintptr_t>(a->aux_out) & 15) == 0);
+    if (a->aux_in) ok = ok && ((reinterpret_cast<uintptr_t>(a->aux_in) & 15) == 0);
+    if (a->add_in) ok = ok && ((reinterpret_cast<uintptr_t>(a->add_in) & 15) == 0);
+    p.vec_ok = ok ? 1 : 0;
+  }
+
+  const int stage_bytes = A_STAGE_BYTES + bn * BLOCK_K * 2;
+  int stages = (g_smem_optin - 1024 - 512) / stage_bytes;
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  if (stages < 2) return set_error("bb_gemm_bf16: not enough shared memory for 2 stages");
+  p.stages = stages;
+  const size_t smem_bytes = (size_t)stages * stage_bytes + 1024 + 512;
+
+  CUtensorMap ta, tb;
+  int e;
+  if (!p.a_mn) e = make_map(&ta, a->A, a->K, a->M, nb1, nb2, a->lda, a->a_s1, a->a_s2, BLOCK_M);
+  else e = make_map(&ta, a->A, a->M, a->K, nb1, nb2, a->lda, a->a_s1, a->a_s2, BLOCK_K);
+  if (e) return e;
+  if (!p.b_mn) e = make_map(&tb, a->B, a->K, a->N, nb1, nb2, a->ldb, a->b_s1, a->b_s2, bn);
+  else e = make_map(&tb, a->B, a->N, a->K, nb1, nb2, a->ldb, a->b_s1, a->b_s2, BLOCK_K);
+  if (e) return e;
+
+  const long long total = (long long)p.m_tiles * p.n_tiles * nb1 * nb2 * p.split_k;
+  if (total > 0x7fffffffLL) return set_error("bb_gemm_bf16: too many tiles");
+  const int grid = total < g_num_sms ? (int)total : g_num_sms;
+  gemm_tc_kernel<<<grid, NUM_THREADS, smem_bytes, stream>>>(ta, tb, p, (int)total);
+  count_launch();
+  return check_launch("gemm_tc_kernel");
+}

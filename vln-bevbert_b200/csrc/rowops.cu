@@ -1,0 +1,699 @@
+// HBM-bound row kernels for the BEVBert encoder stack on sm_100a: casts with dropout, fused
+// (dropout + residual +) LayerNorm forward/backward, masked softmax forward/backward with the graph bias,
+// bias-gradient column sums, embedding sum / scatter, row gather / scatter-add and fused softmax
+// cross-entropy. One warp per row where rows are <= 1024 wide, 16-byte vector accesses, fp32 math,
+// bf16 storage, warp-shuffle reductions; parameter-gradient reductions use per-block partials + atomics.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/bevbert_b200.h"
+#include "common.h"
+#include "ptx.cuh"
+
+namespace bb {
+
+typedef __nv_bfloat16 bf16;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ void load8(const bf16* p, float (&v)[8]) {
+  const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __bfloat1622float2(h[i]);
+    v[2 * i] = f.x;
+    v[2 * i + 1] = f.y;
+  }
+}
+__device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+  v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void store8(bf16* p, const float (&v)[8]) {
+  __align__(16) __nv_bfloat162 h[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+  *reinterpret_cast<uint4*>(p) = *reinterpret_cast<uint4*>(h);
+}
+__device__ __forceinline__ void store8(float* p, const float (&v)[8]) {
+  reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+  reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+}
+
+// ------------------------------------------------------------------------------------- casts
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, long long n, uint64_t seed,
+                                     uint32_t thresh, float scale) {
+  const long long stride = (long long)gridDim.x * blockDim.x * 8;
+  for (long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 8; i < n; i += stride) {
+    if (i + 8 <= n) {
+      float v[8];
+      load8(src + i, v);
+      if (thresh) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = drop_keep(seed, i + j, thresh) ? v[j] * scale : 0.f;
+      }
+      store8(dst + i, v);
+    } else {
+      for (long long j = i; j < n; ++j) {
+        float v = src[j];
+        if (thresh) v = drop_keep(seed, j, thresh) ? v * scale : 0.f;
+        dst[j] = __float2bfloat16(v);
+      }
+    }
+  }
+}
+__global__ void cast_bf16_f32_kernel(const bf16* __restrict__ src, float* __restrict__ dst, long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x * 8;
+  for (long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 8; i < n; i += stride) {
+    if (i + 8 <= n) {
+      float v[8];
+      load8(src + i, v);
+      store8(dst + i, v);
+    } else {
+      for (long long j = i; j < n; ++j) dst[j] = __bfloat162float(src[j]);
+    }
+  }
+}
+__global__ void add_bf16_kernel(const bf16* __restrict__ a, const bf16* __restrict__ b, bf16* __restrict__ out,
+                                long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x * 8;
+  for (long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 8; i < n; i += stride) {
+    if (i + 8 <= n) {
+      float x[8], y[8];
+      load8(a + i, x);
+      load8(b + i, y);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[j] += y[j];
+      store8(out + i, x);
+    } else {
+      for (long long j = i; j < n; ++j) out[j] = __float2bfloat16(__bfloat162float(a[j]) + __bfloat162float(b[j]));
+    }
+  }
+}
+__global__ void axpy_f32_from_bf16_kernel(const bf16* __restrict__ x, float* __restrict__ y, long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += stride)
+    y[i] += __bfloat162float(x[i]);
+}
+
+// ------------------------------------------------------------------------------------- LayerNorm
+constexpr int LN_MAXCH = 4;  // 4 chunks of 256 columns -> H <= 1024
+constexpr int LN_WARPS = 8;
+
+template <typename XT>
+__global__ void __launch_bounds__(LN_WARPS * 32)
+layernorm_fwd_kernel(const XT* __restrict__ x, const bf16* __restrict__ res, const float* __restrict__ gamma,
+                     const float* __restrict__ beta, float eps, long long rows, int H, uint64_t seed_in,
+                     uint32_t thresh_in, float scale_in, uint64_t seed_out, uint32_t thresh_out, float scale_out,
+                     bf16* __restrict__ y, float* __restrict__ y_f32, float* __restrict__ mean_out,
+                     float* __restrict__ rstd_out) {
+  const int lane = threadIdx.x & 31;
+  const long long row = blockIdx.x * (long long)LN_WARPS + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const long long base = row * H;
+  float z[LN_MAXCH][8];
+  float s = 0.f;
+#pragma unroll
+  for (int c = 0; c < LN_MAXCH; ++c) {
+    const int col = c * 256 + lane * 8;
+    if (col < H) {
+      load8(x + base + col, z[c]);
+      if (thresh_in) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) z[c][j] = drop_keep(seed_in, base + col + j, thresh_in) ? z[c][j] * scale_in : 0.f;
+      }
+      if (res) {
+        float r[8];
+        load8(res + base + col, r);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) z[c][j] += r[j];
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += z[c][j];
+    }
+  }
+  const float mean = warp_sum(s) / (float)H;
+  float q = 0.f;
+#pragma unroll
+  for (int c = 0; c < LN_MAXCH; ++c) {
+    const int col = c * 256 + lane * 8;
+    if (col < H) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = z[c][j] - mean;
+        q += d * d;
+      }
+    }
+  }
+  const float var = warp_sum(q) / (float)H;
+  const float rstd = 1.0f / sqrtf(var + eps);
+  if (lane == 0) {
+    if (mean_out) mean_out[row] = mean;
+    if (rstd_out) rstd_out[row] = rstd;
+  }
+#pragma unroll
+  for (int c = 0; c < LN_MAXCH; ++c) {
+    const int col = c * 256 + lane * 8;
+    if (col < H) {
+      float g[8], b[8], o[8];
+      load8(gamma + col, g);
+      load8(beta + col, b);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        o[j] = (z[c][j] - mean) * rstd * g[j] + b[j];
+        if (thresh_out) o[j] = drop_keep(seed_out, base + col + j, thresh_out) ? o[j] * scale_out : 0.f;
+      }
+      if (y) store8(y + base + col, o);
+      if (y_f32) store8(y_f32 + base + col, o);
+    }
+  }
+}
+
+// Backward. Grid-stride over rows (one warp per row); each lane keeps per-column dgamma/dbeta partials,
+// reduced through shared memory and flushed with one atomicAdd per column per block.
+template <typename DYT, typename XT, typename DXT>
+__global__ void __launch_bounds__(LN_WARPS * 32)
+layernorm_bwd_kernel(const DYT* __restrict__ dy, const XT* __restrict__ x, const bf16* __restrict__ res,
+                     const float* __restrict__ gamma, const float* __restrict__ mean_in,
+                     const float* __restrict__ rstd_in, long long rows, int H, uint64_t seed_in, uint32_t thresh_in,
+                     float scale_in, uint64_t seed_out, uint32_t thresh_out, float scale_out, DXT* __restrict__ dx,
+                     bf16* __restrict__ dres, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  __shared__ float sg[LN_MAXCH * 256];
+  __shared__ float sb[LN_MAXCH * 256];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < LN_MAXCH * 256; i += blockDim.x) {
+    sg[i] = 0.f;
+    sb[i] = 0.f;
+  }
+  __syncthreads();
+  float pg[LN_MAXCH][8], pb[LN_MAXCH][8];
+#pragma unroll
+  for (int c = 0; c < LN_MAXCH; ++c)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) pg[c][j] = pb[c][j] = 0.f;
+
+  for (long long row = blockIdx.x * (long long)LN_WARPS + warp; row < rows; row += (long long)gridDim.x * LN_WARPS) {
+    const long long base = row * H;
+    const float mean = mean_in[row], rstd = rstd_in[row];
+    float xh[LN_MAXCH][8], g[LN_MAXCH][8];
+    float c1 = 0.f, c2 = 0.f;
+#pragma unroll
+    for (int c = 0; c < LN_MAXCH; ++c) {
+      const int col = c * 256 + lane * 8;
+      if (col < H) {
+        float z[8], d[8], gm[8];
+        load8(x + base + col, z);
+        if (thresh_in) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) z[j] = drop_keep(seed_in, base + col + j, thresh_in) ? z[j] * scale_in : 0.f;
+        }
+        if (res) {
+          float r[8];
+          load8(res + base + col, r);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) z[j] += r[j];
+        }
+        load8(dy + base + col, d);
+        load8(gamma + col, gm);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (thresh_out) d[j] = drop_keep(seed_out, base + col + j, thresh_out) ? d[j] * scale_out : 0.f;
+          xh[c][j] = (z[j] - mean) * rstd;
+          g[c][j] = d[j] * gm[j];
+          c1 += g[c][j];
+          c2 += g[c][j] * xh[c][j];
+          pg[c][j] += d[j] * xh[c][j];
+          pb[c][j] += d[j];
+        }
+      }
+    }
+    c1 = warp_sum(c1) / (float)H;
+    c2 = warp_sum(c2) / (float)H;
+#pragma unroll
+    for (int c = 0; c < LN_MAXCH; ++c) {
+      const int col = c * 256 + lane * 8;
+      if (col < H) {
+        float dz[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dz[j] = rstd * (g[c][j] - c1 - xh[c][j] * c2);
+        if (dres) store8(dres + base + col, dz);
+        if (dx) {
+          if (thresh_in) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dz[j] = drop_keep(seed_in, base + col + j, thresh_in) ? dz[j] * scale_in : 0.f;
+          }
+          store8(dx + base + col, dz);
+        }
+      }
+    }
+  }
+  if (dgamma || dbeta) {
+#pragma unroll
+    for (int c = 0; c < LN_MAXCH; ++c) {
+      const int col = c * 256 + lane * 8;
+      if (col < H) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          atomicAdd(&sg[col + j], pg[c][j]);
+          atomicAdd(&sb[col + j], pb[c][j]);
+        }
+      }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < H; i += blockDim.x) {
+      if (dgamma) atomicAdd(dgamma + i, sg[i]);
+      if (dbeta) atomicAdd(dbeta + i, sb[i]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------- column sums
+__global__ void __launch_bounds__(256)
+colsum_bf16_kernel(const bf16* __restrict__ x, long long rows, int N, long long ld, float* __restrict__ out) {
+  // blockDim = (32, 8): 32 lanes x 8 columns each = 256 columns per block in x; rows strided over y and grid.y
+  __shared__ float part[8][256];
+  const int col = blockIdx.x * 256 + threadIdx.x * 8;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  if (col < N) {
+    const bool vec = (col + 8 <= N) && (ld % 8 == 0);
+    for (long long r = blockIdx.y * 8 + threadIdx.y; r < rows; r += (long long)gridDim.y * 8) {
+      if (vec) {
+        float v[8];
+        load8(x + r * ld + col, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += v[j];
+      } else {
+        for (int j = 0; j < 8; ++j)
+          if (col + j < N) acc[j] += __bfloat162float(x[r * ld + col + j]);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) part[threadIdx.y][threadIdx.x * 8 + j] = acc[j];
+  __syncthreads();
+  const int t = threadIdx.y * 32 + threadIdx.x;
+  float s = 0.f;
+#pragma unroll
+  for (int yy = 0; yy < 8; ++yy) s += part[yy][t];
+  const int c = blockIdx.x * 256 + t;
+  if (c < N) atomicAdd(out + c, s);
+}
+
+// ------------------------------------------------------------------------------------- softmax
+template <int MAXE>
+__global__ void __launch_bounds__(256)
+softmax_fwd_kernel(const float* __restrict__ scores, const float* __restrict__ kmask, const float* __restrict__ bias,
+                   long long nrows, int H, int nq, int nk, int ld, uint64_t seed, uint32_t thresh, float scale,
+                   bf16* __restrict__ probs, bf16* __restrict__ probs_drop) {
+  const int lane = threadIdx.x & 31;
+  const long long row = blockIdx.x * 8LL + (threadIdx.x >> 5);
+  if (row >= nrows) return;
+  const int q = row % nq;
+  const long long b = row / ((long long)nq * H);
+  const float* s = scores + row * ld;
+  const float* km = kmask ? kmask + b * nk : nullptr;
+  const float* bs = bias ? bias + (b * nq + q) * nk : nullptr;
+  float v[MAXE];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int e = 0; e < MAXE; ++e) {
+    const int k = e * 32 + lane;
+    float t = -INFINITY;
+    if (k < nk) {
+      t = s[k];
+      if (km) t += km[k];
+      if (bs) t += bs[k];
+    }
+    v[e] = t;
+    mx = fmaxf(mx, t);
+  }
+  mx = warp_max(mx);
+  float sum = 0.f;
+#pragma unroll
+  for (int e = 0; e < MAXE; ++e) {
+    const int k = e * 32 + lane;
+    const float ex = (k < nk) ? __expf(v[e] - mx) : 0.f;
+    v[e] = ex;
+    sum += ex;
+  }
+  sum = warp_sum(sum);
+  const float inv = 1.0f / sum;
+  bf16* p = probs + row * ld;
+  bf16* pd = probs_drop ? probs_drop + row * ld : nullptr;
+#pragma unroll
+  for (int e = 0; e < MAXE; ++e) {
+    const int k = e * 32 + lane;
+    if (k < ld) {
+      const float pr = (k < nk) ? v[e] * inv : 0.f;
+      p[k] = __float2bfloat16(pr);
+      if (pd) {
+        float t = pr;
+        if (thresh) t = drop_keep(seed, row * ld + k, thresh) ? pr * scale : 0.f;
+        pd[k] = __float2bfloat16(t);
+      }
+    }
+  }
+}
+
+template <int MAXE>
+__global__ void __launch_bounds__(256)
+softmax_bwd_kernel(const bf16* __restrict__ probs, const float* __restrict__ dprobs, long long nrows, int H, int nq,
+                   int nk, int ld, uint64_t seed, uint32_t thresh, float scale, float out_scale, bf16* __restrict__ ds,
+                   float* __restrict__ dbias) {
+  const int lane = threadIdx.x & 31;
+  const long long row = blockIdx.x * 8LL + (threadIdx.x >> 5);
+  if (row >= nrows) return;
+  const int q = row % nq;
+  const long long b = row / ((long long)nq * H);
+  const bf16* p = probs + row * ld;
+  const float* dp = dprobs + row * ld;
+  float pv[MAXE], g[MAXE];
+  float dot = 0.f;
+#pragma unroll
+  for (int e = 0; e < MAXE; ++e) {
+    const int k = e * 32 + lane;
+    pv[e] = 0.f;
+    g[e] = 0.f;
+    if (k < nk) {
+      pv[e] = __bfloat162float(p[k]);
+      float t = dp[k];
+      if (thresh) t = drop_keep(seed, row * ld + k, thresh) ? t * scale : 0.f;
+      g[e] = t;
+      dot += pv[e] * t;
+    }
+  }
+  dot = warp_sum(dot);
+  bf16* o = ds + row * ld;
+  float* db = dbias ? dbias + (b * nq + q) * nk : nullptr;
+#pragma unroll
+  for (int e = 0; e < MAXE; ++e) {
+    const int k = e * 32 + lane;
+    if (k < ld) {
+      const float d = (k < nk) ? pv[e] * (g[e] - dot) : 0.f;
+      o[k] = __float2bfloat16(d * out_scale);
+      if (db && k < nk) atomicAdd(db + k, d);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------- embeddings
+__global__ void embed_sum_kernel(const int64_t* __restrict__ ids, const float* __restrict__ word,
+                                 const float* __restrict__ pos, const float* __restrict__ type0, long long ntok, int L,
+                                 int H, float* __restrict__ out) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;  // over ntok * H/4
+  const int h4 = H / 4;
+  if (i >= ntok * h4) return;
+  const long long tok = i / h4;
+  const int c = (i % h4) * 4;
+  const int l = tok % L;
+  const float4 w = __ldg(reinterpret_cast<const float4*>(word + ids[tok] * H + c));
+  const float4 p = __ldg(reinterpret_cast<const float4*>(pos + (long long)l * H + c));
+  const float4 t = __ldg(reinterpret_cast<const float4*>(type0 + c));
+  float4 o;
+  o.x = (w.x + p.x) + t.x;
+  o.y = (w.y + p.y) + t.y;
+  o.z = (w.z + p.z) + t.z;
+  o.w = (w.w + p.w) + t.w;
+  *reinterpret_cast<float4*>(out + tok * H + c) = o;
+}
+__global__ void embed_scatter_grad_kernel(const int64_t* __restrict__ ids, const float* __restrict__ dz, long long ntok,
+                                          int L, int H, int64_t padding_idx, float* __restrict__ dword,
+                                          float* __restrict__ dpos, float* __restrict__ dtype0) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= ntok * H) return;
+  const long long tok = i / H;
+  const int c = i % H;
+  const int l = tok % L;
+  const float g = dz[i];
+  const int64_t id = ids[tok];
+  if (dword && id != padding_idx) atomicAdd(dword + id * H + c, g);
+  if (dpos) atomicAdd(dpos + (long long)l * H + c, g);
+  if (dtype0) atomicAdd(dtype0 + c, g);
+}
+
+// ------------------------------------------------------------------------------------- gather / scatter rows
+__global__ void gather_rows_bf16_kernel(const bf16* __restrict__ in, const int64_t* __restrict__ idx, long long nout,
+                                        int H, bf16* __restrict__ out) {
+  const int h8 = H / 8;
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= nout * h8) return;
+  const long long r = i / h8;
+  const int c = (i % h8) * 8;
+  const int64_t src = idx[r];
+  uint4 v = make_uint4(0, 0, 0, 0);
+  if (src >= 0) v = __ldg(reinterpret_cast<const uint4*>(in + src * H + c));
+  *reinterpret_cast<uint4*>(out + r * H + c) = v;
+}
+__global__ void scatter_add_rows_kernel(const bf16* __restrict__ in, const int64_t* __restrict__ idx, long long nin,
+                                        int H, float* __restrict__ out) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= nin * H) return;
+  const long long r = i / H;
+  const int c = i % H;
+  const int64_t dst = idx[r];
+  if (dst >= 0) atomicAdd(out + dst * H + c, __bfloat162float(in[i]));
+}
+
+// ------------------------------------------------------------------------------------- softmax cross entropy
+__global__ void __launch_bounds__(256)
+softmax_xent_kernel(const float* __restrict__ logits, const int64_t* __restrict__ labels, int V, long long ld,
+                    float* __restrict__ loss, const float* __restrict__ gscale, bf16* __restrict__ dlogits) {
+  __shared__ float red[8];
+  __shared__ float bcast;
+  const long long row = blockIdx.x;
+  const float* x = logits + row * ld;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t lab = labels[row];
+  float mx = -INFINITY;
+  for (int i = threadIdx.x; i < V; i += 256) mx = fmaxf(mx, x[i]);
+  mx = warp_max(mx);
+  if (lane == 0) red[warp] = mx;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float m = red[0];
+    for (int i = 1; i < 8; ++i) m = fmaxf(m, red[i]);
+    bcast = m;
+  }
+  __syncthreads();
+  mx = bcast;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < V; i += 256) s += __expf(x[i] - mx);
+  s = warp_sum(s);
+  __syncthreads();
+  if (lane == 0) red[warp] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += red[i];
+    bcast = t;
+  }
+  __syncthreads();
+  s = bcast;
+  const bool valid = lab >= 0 && lab < V;
+  if (threadIdx.x == 0) loss[row] = valid ? (logf(s) + mx - x[lab]) : 0.f;
+  if (dlogits) {
+    const float gs = valid ? (gscale ? gscale[row] : 1.f) : 0.f;
+    const float inv = 1.0f / s;
+    bf16* d = dlogits + row * ld;
+    for (int i = threadIdx.x; i < ld; i += 256) {
+      float g = 0.f;
+      if (i < V) g = (__expf(x[i] - mx) * inv - (i == lab ? 1.f : 0.f)) * gs;
+      d[i] = __float2bfloat16(g);
+    }
+  }
+}
+
+static inline unsigned grid1d(long long n, int per_block, int cap = 148 * 16) {
+  long long g = (n + per_block - 1) / per_block;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (unsigned)g;
+}
+
+}  // namespace bb
+
+using namespace bb;
+#define STREAM ((cudaStream_t)stream)
+
+extern "C" int bb_cast_f32_bf16(const float* src, void* dst, int64_t n, uint64_t seed, uint32_t thresh, float scale,
+                                void* stream) {
+  if (n <= 0) return 0;
+  if (((uintptr_t)src & 15) || ((uintptr_t)dst & 15)) return set_error("bb_cast_f32_bf16: pointers must be 16B aligned");
+  cast_f32_bf16_kernel<<<grid1d(n, 256 * 8), 256, 0, STREAM>>>(src, (bf16*)dst, n, seed, thresh, scale);
+  count_launch();
+  return check_launch("cast_f32_bf16_kernel");
+}
+extern "C" int bb_cast_bf16_f32(const void* src, float* dst, int64_t n, void* stream) {
+  if (n <= 0) return 0;
+  if (((uintptr_t)src & 15) || ((uintptr_t)dst & 15)) return set_error("bb_cast_bf16_f32: pointers must be 16B aligned");
+  cast_bf16_f32_kernel<<<grid1d(n, 256 * 8), 256, 0, STREAM>>>((const bf16*)src, dst, n);
+  count_launch();
+  return check_launch("cast_bf16_f32_kernel");
+}
+extern "C" int bb_add_bf16(const void* a, const void* b, void* out, int64_t n, void* stream) {
+  if (n <= 0) return 0;
+  if (((uintptr_t)a & 15) || ((uintptr_t)b & 15) || ((uintptr_t)out & 15))
+    return set_error("bb_add_bf16: pointers must be 16B aligned");
+  add_bf16_kernel<<<grid1d(n, 256 * 8), 256, 0, STREAM>>>((const bf16*)a, (const bf16*)b, (bf16*)out, n);
+  count_launch();
+  return check_launch("add_bf16_kernel");
+}
+extern "C" int bb_axpy_f32_from_bf16(const void* x, float* y, int64_t n, void* stream) {
+  if (n <= 0) return 0;
+  axpy_f32_from_bf16_kernel<<<grid1d(n, 256), 256, 0, STREAM>>>((const bf16*)x, y, n);
+  count_launch();
+  return check_launch("axpy_f32_from_bf16_kernel");
+}
+
+extern "C" int bb_layernorm_fwd(const void* x, int x_f32, const void* residual, const float* gamma, const float* beta,
+                                float eps, int64_t rows, int H, uint64_t seed_in, uint32_t thresh_in, float scale_in,
+                                uint64_t seed_out, uint32_t thresh_out, float scale_out, void* y, float* y_f32,
+                                float* mean, float* rstd, void* stream) {
+  if (rows <= 0) return 0;
+  if (H % 8 != 0 || H > LN_MAXCH * 256) return set_error("bb_layernorm_fwd: H must be a multiple of 8 and <= 1024");
+  const unsigned grid = (unsigned)((rows + LN_WARPS - 1) / LN_WARPS);
+  if (x_f32)
+    layernorm_fwd_kernel<float><<<grid, LN_WARPS * 32, 0, STREAM>>>(
+        (const float*)x, (const bf16*)residual, gamma, beta, eps, rows, H, seed_in, thresh_in, scale_in, seed_out,
+        thresh_out, scale_out, (bf16*)y, y_f32, mean, rstd);
+  else
+    layernorm_fwd_kernel<bf16><<<grid, LN_WARPS * 32, 0, STREAM>>>(
+        (const bf16*)x, (const bf16*)residual, gamma, beta, eps, rows, H, seed_in, thresh_in, scale_in, seed_out,
+        thresh_out, scale_out, (bf16*)y, y_f32, mean, rstd);
+  count_launch();
+  return check_launch("layernorm_fwd_kernel");
+}
+
+extern "C" int bb_layernorm_bwd(const void* dy, int dy_f32, const void* x, int x_f32, const void* residual,
+                                const float* gamma, const float* mean, const float* rstd, int64_t rows, int H,
+                                uint64_t seed_in, uint32_t thresh_in, float scale_in, uint64_t seed_out,
+                                uint32_t thresh_out, float scale_out, void* dx, int dx_f32, void* dres, float* dgamma,
+                                float* dbeta, void* stream) {
+  if (rows <= 0) return 0;
+  if (H % 8 != 0 || H > LN_MAXCH * 256) return set_error("bb_layernorm_bwd: H must be a multiple of 8 and <= 1024");
+  long long g = (rows + LN_WARPS - 1) / LN_WARPS;
+  if (g > 148 * 4) g = 148 * 4;
+  const unsigned grid = (unsigned)g;
+#define LN_BWD(DYT, XT, DXT)                                                                                        \
+  layernorm_bwd_kernel<DYT, XT, DXT><<<grid, LN_WARPS * 32, 0, STREAM>>>(                                           \
+      (const DYT*)dy, (const XT*)x, (const bf16*)residual, gamma, mean, rstd, rows, H, seed_in, thresh_in, scale_in, \
+      seed_out, thresh_out, scale_out, (DXT*)dx, (bf16*)dres, dgamma, dbeta)
+  if (!dy_f32 && !x_f32 && !dx_f32) LN_BWD(bf16, bf16, bf16);
+  else if (!dy_f32 && x_f32 && dx_f32) LN_BWD(bf16, float, float);
+  else if (dy_f32 && !x_f32 && !dx_f32) LN_BWD(float, bf16, bf16);
+  else if (dy_f32 && x_f32 && dx_f32) LN_BWD(float, float, float);
+  else if (!dy_f32 && !x_f32 && dx_f32) LN_BWD(bf16, bf16, float);
+  else if (!dy_f32 && x_f32 && !dx_f32) LN_BWD(bf16, float, bf16);
+  else return set_error("bb_layernorm_bwd: unsupported dtype combination");
+#undef LN_BWD
+  count_launch();
+  return check_launch("layernorm_bwd_kernel");
+}
+
+extern "C" int bb_colsum_bf16(const void* x, int64_t rows, int N, int64_t ld, float* out, void* stream) {
+  if (rows <= 0 || N <= 0) return 0;
+  long long gy = (rows + 63) / 64;
+  if (gy > 64) gy = 64;
+  dim3 grid((N + 255) / 256, (unsigned)gy);
+  colsum_bf16_kernel<<<grid, dim3(32, 8), 0, STREAM>>>((const bf16*)x, rows, N, ld, out);
+  count_launch();
+  return check_launch("colsum_bf16_kernel");
+}
+
+extern "C" int bb_softmax_fwd(const float* scores, const float* kmask, const float* bias, int nbatch, int H, int nq,
+                              int nk, int ld, uint64_t seed, uint32_t thresh, float scale, void* probs,
+                              void* probs_drop, void* stream) {
+  const long long nrows = (long long)nbatch * H * nq;
+  if (nrows <= 0) return 0;
+  if (ld < nk || ld > 1024) return set_error("bb_softmax_fwd: need nk <= ld <= 1024");
+  const unsigned grid = (unsigned)((nrows + 7) / 8);
+  if (ld <= 128)
+    softmax_fwd_kernel<4><<<grid, 256, 0, STREAM>>>(scores, kmask, bias, nrows, H, nq, nk, ld, seed, thresh, scale,
+                                                    (bf16*)probs, (bf16*)probs_drop);
+  else if (ld <= 512)
+    softmax_fwd_kernel<16><<<grid, 256, 0, STREAM>>>(scores, kmask, bias, nrows, H, nq, nk, ld, seed, thresh, scale,
+                                                     (bf16*)probs, (bf16*)probs_drop);
+  else
+    softmax_fwd_kernel<32><<<grid, 256, 0, STREAM>>>(scores, kmask, bias, nrows, H, nq, nk, ld, seed, thresh, scale,
+                                                     (bf16*)probs, (bf16*)probs_drop);
+  count_launch();
+  return check_launch("softmax_fwd_kernel");
+}
+
+extern "C" int bb_softmax_bwd(const void* probs, const float* dprobs, int nbatch, int H, int nq, int nk, int ld,
+                              uint64_t seed, uint32_t thresh, float scale, float out_scale, void* ds, float* dbias,
+                              void* stream) {
+  const long long nrows = (long long)nbatch * H * nq;
+  if (nrows <= 0) return 0;
+  if (ld < nk || ld > 1024) return set_error("bb_softmax_bwd: need nk <= ld <= 1024");
+  const unsigned grid = (unsigned)((nrows + 7) / 8);
+  if (ld <= 128)
+    softmax_bwd_kernel<4><<<grid, 256, 0, STREAM>>>((const bf16*)probs, dprobs, nrows, H, nq, nk, ld, seed, thresh,
+                                                    scale, out_scale, (bf16*)ds, dbias);
+  else if (ld <= 512)
+    softmax_bwd_kernel<16><<<grid, 256, 0, STREAM>>>((const bf16*)probs, dprobs, nrows, H, nq, nk, ld, seed, thresh,
+                                                     scale, out_scale, (bf16*)ds, dbias);
+  else
+    softmax_bwd_kernel<32><<<grid, 256, 0, STREAM>>>((const bf16*)probs, dprobs, nrows, H, nq, nk, ld, seed, thresh,
+                                                     scale, out_scale, (bf16*)ds, dbias);
+  count_launch();
+  return check_launch("softmax_bwd_kernel");
+}
+
+extern "C" int bb_embed_sum(const int64_t* ids, const float* word, const float* pos, const float* type0, int64_t ntok,
+                            int L, int H, float* out, void* stream) {
+  if (ntok <= 0) return 0;
+  if (H % 4 != 0) return set_error("bb_embed_sum: H must be a multiple of 4");
+  const long long n = ntok * (H / 4);
+  embed_sum_kernel<<<(unsigned)((n + 255) / 256), 256, 0, STREAM>>>(ids, word, pos, type0, ntok, L, H, out);
+  count_launch();
+  return check_launch("embed_sum_kernel");
+}
+extern "C" int bb_embed_scatter_grad(const int64_t* ids, const float* dz, int64_t ntok, int L, int H,
+                                     int64_t padding_idx, float* dword, float* dpos, float* dtype0, void* stream) {
+  if (ntok <= 0) return 0;
+  const long long n = ntok * H;
+  embed_scatter_grad_kernel<<<(unsigned)((n + 255) / 256), 256, 0, STREAM>>>(ids, dz, ntok, L, H, padding_idx, dword,
+                                                                             dpos, dtype0);
+  count_launch();
+  return check_launch("embed_scatter_grad_kernel");
+}
+
+extern "C" int bb_gather_rows_bf16(const void* in, const int64_t* idx, int64_t nout, int H, void* out, void* stream) {
+  if (nout <= 0) return 0;
+  if (H % 8 != 0) return set_error("bb_gather_rows_bf16: H must be a multiple of 8");
+  const long long n = nout * (H / 8);
+  gather_rows_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, STREAM>>>((const bf16*)in, idx, nout, H, (bf16*)out);
+  count_launch();
+  return check_launch("gather_rows_bf16_kernel");
+}
+extern "C" int bb_scatter_add_rows(const void* in_bf16, const int64_t* idx, int64_t nin, int H, float* out_f32,
+                                   void* stream) {
+  if (nin <= 0) return 0;
+  const long long n = nin * H;
+  scatter_add_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, STREAM>>>((const bf16*)in_bf16, idx, nin, H, out_f32);
+  count_launch();
+  return check_launch("scatter_add_rows_kernel");
+}
+
+extern "C" int bb_softmax_xent(const float* logits, const int64_t* labels, int64_t rows, int V, int64_t ld, float* loss,
+                               const float* gscale, void* dlogits, void* stream) {
+  if (rows <= 0) return 0;
+  softmax_xent_kernel<<<(unsigned)rows, 256, 0, STREAM>>>(logits, labels, V, ld, loss, gscale, (bf16*)dlogits);
+  count_launch();
+  return check_launch("softmax_xent_kernel");
+}
