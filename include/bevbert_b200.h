@@ -55,7 +55,10 @@ typedef struct bb_gemm_args {
   void* aux_out;     /* bf16, same strides as D: pre-activation (alpha*acc+bias) or NULL */
   const void* aux_in; /* bf16, same strides as D, or NULL */
   int32_t epi_mul;   /* 0 none; 1: result *= gelu'(aux_in); 2: result *= (aux_in > 0) */
-  const void* add_in; /* bf16, same strides as D, or NULL: result += add_in (after act/epi_mul) */
+  uint64_t drop_seed;  /* inverted dropout on the result (after act / epi_mul, before add_in); */
+  uint32_t drop_thresh; /*   keep iff rng(seed, output element offset) >= thresh; 0 = no dropout   */
+  float drop_scale;     /*   1/(1-p)                                                              */
+  const void* add_in; /* bf16, same strides as D, or NULL: result += add_in (last) */
   int32_t block_n;   /* 0 = pick automatically; else N tile (multiple of 16, of 64 when b_mn) */
 } bb_gemm_args;
 
@@ -137,6 +140,26 @@ int bb_embed_scatter_grad(const int64_t* ids, const float* dz, int64_t ntok, int
  * out[idx[r], :] += in[r, :] in f32. */
 int bb_gather_rows_bf16(const void* in, const int64_t* idx, int64_t nout, int H, void* out, void* stream);
 int bb_scatter_add_rows(const void* in_bf16, const int64_t* idx, int64_t nin, int H, float* out_f32, void* stream);
+
+/* bf16 -> bf16 inverted dropout with the same counter-based RNG as everywhere else (element index = counter):
+ * regenerates a forward mask in backward.  src may equal dst. */
+int bb_dropout_bf16(const void* src, void* dst, int64_t n, uint64_t seed, uint32_t thresh, float scale, void* stream);
+/* out[r,:] = a[r,:] (+ b[r,:]) (+ table[idx[r],:]) (+ vec[:]) ; a,b,out bf16 (rows,H); table,vec f32; idx int64.
+ * (embedding sums of vilmodel.py:521-524, 590-592, 675-677). b/table/idx/vec may be NULL. */
+int bb_add_rows(const void* a, const void* b, const float* table, const int64_t* idx, const float* vec, int64_t rows,
+                int H, void* out, void* stream);
+/* in-place x[r,:] *= g[r] on a bf16 (rows, ld) matrix. */
+int bb_scale_rows_bf16(void* x, const float* g, int64_t rows, int64_t ld, void* stream);
+/* Segment weighted sum (vilmodel.py:632-666 _aggregate_gmap_features, host loops turned into CSR lists):
+ * out[s,:] = sum_{e in [seg_off[s], seg_off[s+1])} w[e] * src[idx[e],:]  (src,out bf16; f32 accumulate).
+ * Backward: dsrc_f32[idx[e],:] += w[e] * dout[s,:] (atomics; caller zeroes dsrc). */
+int bb_segment_wsum(const void* src, const int32_t* seg_off, const int32_t* idx, const float* w, int64_t nseg, int H,
+                    void* out, void* stream);
+int bb_segment_wsum_bwd(const void* dout, const int32_t* seg_off, const int32_t* idx, const float* w, int64_t nseg,
+                        int H, float* dsrc_f32, void* stream);
+
+/* out = dy * f'(aux): mode 1 = exact-erf GELU derivative at aux (pre-activation), mode 2 = (aux > 0) (ReLU). */
+int bb_act_bwd_bf16(const void* dy, const void* aux, int mode, void* out, int64_t n, void* stream);
 
 /* Generic small elementwise helpers on bf16 tensors. */
 int bb_add_bf16(const void* a, const void* b, void* out, int64_t n, void* stream);       /* out = a + b */

@@ -1,0 +1,338 @@
+"""Per-kernel parity on the GPU, through the C ABI (bevbert_b200.kernels -> ctypes -> libbevbert_b200.so).
+
+Each kernel is compared with its torch restatement (tests/emu_kernels.py, fp32 on CPU) on the same
+bf16-rounded inputs.  Tolerances: integer / index work bit-exact; fp32 outputs 1e-4 relative;
+bf16 outputs 1e-2 relative (one bf16 rounding = 2^-9)."""
+import math
+
+import pytest
+import torch
+
+import emu_kernels as E
+from helpers import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+BF = torch.bfloat16
+
+
+@pytest.fixture(scope="module")
+def K():
+    import bevbert_b200.kernels as K
+    assert torch.cuda.is_available()
+    return K
+
+
+def rnd(*shape, scale=1.0, dtype=BF, seed=0):
+    g = torch.Generator().manual_seed(seed + sum(shape))
+    return (torch.randn(*shape, generator=g) * scale).to(dtype)
+
+
+def dev(t):
+    return t.cuda() if t is not None else None
+
+
+def f32(t):
+    return t.float().cpu() if t is not None else None
+
+
+# ----------------------------------------------------------------------------------------- BEV
+def test_lift_index_bit_exact(K):
+    from bevbert_b200 import synth
+    from oracle import bevbert_ref as R
+    for D, res in ((21, 0.5), (11, 1.0)):
+        b = synth.make_batch(synth.SynthConfig(batch_size=3, bev_dim=D, bev_res=res), seed=5)
+        idx, pc = K.bev_lift_index(dev(b["depths"]).reshape(3, 12, 14, 14), dev(b["T_c2w"]), dev(b["S_w2c"]).reshape(3, 3),
+                                   dev(b["T_w2c"]).reshape(3, 4, 4), D, res, want_pc=True)
+        rpc, nod = R.lift_points(b["depths"], b["T_c2w"], b["S_w2c"], b["T_w2c"])
+        ridx = R.cell_index(rpc, nod, D, res)
+        assert torch.equal(pc.cpu(), rpc), "ego-frame point cloud must match the oracle bit for bit"
+        assert torch.equal(idx.cpu().long(), ridx), "cell indices must be bit-exact"
+        assert (ridx >= 0).float().mean() > 0.3
+
+
+def test_lift_index_known_answers(K):
+    """Hand-built cases: centre cell, round-half-even at +-0.25 m, y clip, zero depth, outside."""
+    D, res = 21, 0.5
+
+    def cell_of(x, y, z):
+        # one pixel image whose un-projection is (x*?..): use T_c2w translation to place the point, depth tiny
+        T = torch.eye(4)
+        T[0, 3], T[1, 3], T[2, 3] = x, y, z
+        depths = torch.full((1, 1, 1, 1), 1e-30)          # non-zero depth, negligible offset
+        idx, _ = K.bev_lift_index(dev(depths), dev(T[None, None]), dev(torch.zeros(1, 3)), dev(torch.eye(4)[None]), D,
+                                  res, fx=1.0, fy=1.0, cx=0.5, cy=0.5)
+        return int(idx.cpu()[0, 0])
+    centre = (D * D - 1) // 2
+    assert cell_of(0, 0, 0) == centre
+    assert cell_of(0.25, 0, 0) == centre          # 0.25/0.5+10 = 10.5 -> rounds to even 10
+    assert cell_of(0.75, 0, 0) == centre + 2      # 11.5 -> 12
+    assert cell_of(-0.25, 0, 0) == centre         # 9.5 -> 10 (even)
+    assert cell_of(0, 0.5, 0) == centre           # y == clip is kept
+    assert cell_of(0, 0.5001, 0) == -1            # above the clip
+    assert cell_of(5.3, 0, 0) == -1               # 20.6 -> 21 >= D: outside
+    assert cell_of(0, 0, -5.3) == -1
+    z = torch.zeros(1, 1, 1, 1)
+    idx, _ = K.bev_lift_index(dev(z), dev(torch.eye(4)[None, None]), dev(torch.zeros(1, 3)), dev(torch.eye(4)[None]), D,
+                              res)
+    assert int(idx.cpu()[0, 0]) == -1             # depth 0 dropped
+
+
+def test_scatter_mean_deterministic_and_exact(K):
+    B, P, C, ncell = 3, 2352, 768, 441
+    g = torch.Generator().manual_seed(1)
+    feats = torch.randn(B, P, C, generator=g)
+    idx = torch.randint(-1, ncell, (B, P), generator=g, dtype=torch.int32)
+    idx[0, :50] = 7                      # heavily shared cell
+    idx[1] = -1                          # sample with no valid point
+    idx[2, idx[2] == 5] = 6              # guaranteed empty cell
+    o32, o16, ob, cnt = K.bev_scatter_mean(dev(feats), dev(idx), ncell)
+    r32, _, rob, rcnt = E.bev_scatter_mean(feats, idx, ncell)
+    assert torch.equal(o32.cpu(), r32), "sequential-order sum + divide must be bit-exact"
+    assert torch.equal(ob.cpu(), rob) and torch.equal(cnt.cpu(), rcnt)
+    assert torch.equal(o16.cpu(), r32.to(BF))
+    assert not ob.cpu()[1].any() and float(o32[1].abs().max()) == 0.0
+    o32b, _, _, _ = K.bev_scatter_mean(dev(feats), dev(idx), ncell)
+    assert torch.equal(o32, o32b), "run-to-run deterministic"
+    sems = torch.nn.functional.one_hot(torch.randint(0, 40, (B, P), generator=g), 40).double()
+    s, sm = K.bev_scatter_sem(dev(sems), dev(idx), ncell)
+    rs, rsm = E.bev_scatter_sem(sems, idx, ncell)
+    assert torch.equal(s.cpu(), rs) and torch.equal(sm.cpu(), rsm)
+
+
+# ----------------------------------------------------------------------------------------- casts / dropout
+def test_cast_and_dropout(K):
+    x = torch.randn(1000003)
+    y = K.cast_to_act(dev(x))
+    assert torch.equal(y.cpu(), x.to(BF))
+    assert torch.equal(K.cast_to_f32(y).cpu(), x.to(BF).float())
+    p = 0.1
+    th, sc = K.drop_params(p)
+    d1 = K.cast_to_act(dev(x), (1234, th, sc)).cpu().float()
+    d2 = K.cast_to_act(dev(x), (1234, th, sc)).cpu().float()
+    d3 = K.cast_to_act(dev(x), (1235, th, sc)).cpu().float()
+    assert torch.equal(d1, d2) and not torch.equal(d1, d3)
+    keep = d1 != 0
+    assert abs(float(keep.float().mean()) - (1 - p)) < 3e-3
+    assert torch.equal(d1[keep], (x * sc).to(BF).float()[keep])
+    # the bf16->bf16 dropout regenerates the same mask
+    d4 = K.dropout_act(y, (1234, th, sc)).cpu().float()
+    nz = (y.cpu().float() != 0) & (x != 0)
+    assert torch.equal((d4 != 0)[nz], keep[nz])
+
+
+# ----------------------------------------------------------------------------------------- LayerNorm
+@pytest.mark.parametrize("x_f32,res", [(False, True), (False, False), (True, False)])
+def test_layernorm_fwd_bwd(K, x_f32, res):
+    rows, H = 1037, 768
+    x = rnd(rows, H, dtype=torch.float32 if x_f32 else BF)
+    r = rnd(rows, H, seed=1) if res else None
+    gam, bet = torch.rand(H) + 0.5, torch.randn(H) * 0.1
+    dy = rnd(rows, H, seed=2)
+    y, y32, mean, rstd = K.layernorm_fwd(dev(x), dev(r), dev(gam), dev(bet), 1e-12, want_f32=True)
+    ry, _, rm, rr = E.layernorm_fwd(f32(x), f32(r), gam, bet, 1e-12)
+    assert rel_l2(y32, ry) < 1e-5 and rel_l2(y, ry) < 5e-3
+    assert rel_l2(mean, rm) < 1e-5 and rel_l2(rstd, rr) < 1e-5
+    dg, db = torch.zeros(H).cuda(), torch.zeros(H).cuda()
+    dx, dres = K.layernorm_bwd(dev(dy), dev(x), dev(r), dev(gam), mean, rstd, want_dres=res, dx_f32=x_f32, dgamma=dg,
+                               dbeta=db)
+    rdg, rdb = torch.zeros(H), torch.zeros(H)
+    rdx, rdres = E.layernorm_bwd(f32(dy), f32(x), f32(r), gam, rm, rr, want_dres=res, dgamma=rdg, dbeta=rdb)
+    assert rel_l2(dx, rdx) < (1e-4 if x_f32 else 6e-3)
+    if res:
+        assert rel_l2(dres, rdres) < 6e-3
+    assert rel_l2(dg, rdg) < 1e-4 and rel_l2(db, rdb) < 1e-4
+
+
+def test_layernorm_dropout_replay(K):
+    rows, H = 512, 768
+    x, r = rnd(rows, H), rnd(rows, H, seed=1)
+    gam, bet = torch.ones(H), torch.zeros(H)
+    th, sc = K.drop_params(0.1)
+    di, do = (77, th, sc), (78, th, sc)
+    y, _, mean, rstd = K.layernorm_fwd(dev(x), dev(r), dev(gam), dev(bet), 1e-12, drop_in=di, drop_out=do)
+    out_keep = (y.cpu().float() != 0)
+    assert abs(float(out_keep.float().mean()) - 0.9) < 5e-3
+    # backward with dy = 1 : dx must vanish exactly where the input mask dropped x
+    xin = K.dropout_act(dev(x), di).cpu().float()
+    dy = torch.ones(rows, H).to(BF)
+    dx, dres = K.layernorm_bwd(dev(dy), dev(x), dev(r), dev(gam), mean, rstd, drop_in=di, drop_out=do, want_dres=True)
+    dropped = (xin == 0) & (x.float() != 0)
+    assert float(dx.cpu().float()[dropped].abs().max()) == 0.0
+    kept = ~dropped
+    assert torch.allclose(dx.cpu().float()[kept], (dres.cpu().float() * sc)[kept], rtol=2e-2, atol=1e-3)
+
+
+# ----------------------------------------------------------------------------------------- reductions / softmax
+def test_colsum(K):
+    x = rnd(3001, 2304)
+    assert rel_l2(K.colsum(dev(x), 2304), E.colsum(f32(x), 2304)) < 1e-5
+    x = rnd(77, 40)
+    assert rel_l2(K.colsum(dev(x), 40), E.colsum(f32(x), 40)) < 1e-5
+
+
+@pytest.mark.parametrize("nq,nk,neg", [(441, 441, -10000.0), (20, 80, -10000.0), (36, 36, float("-inf")), (80, 491, -10000.0)])
+def test_softmax_fwd_bwd(K, nq, nk, neg):
+    B, H = 3, 12
+    ld = (nk + 7) // 8 * 8
+    s = torch.randn(B, H, nq, ld) * 2
+    kmask = torch.zeros(B, nk)
+    kmask[1, nk // 2:] = neg
+    bias = torch.randn(B, nq, nk) * 0.5
+    p, pd = K.softmax_fwd(dev(s), dev(kmask), dev(bias), B, H, nq, nk, ld)
+    rp, _ = E.softmax_fwd(s, kmask, bias, B, H, nq, nk, ld)
+    assert rel_l2(p, rp) < 4e-3
+    assert float(p.cpu().float()[..., nk:].abs().max() if ld > nk else 0.0) == 0.0
+    dp = torch.randn(B, H, nq, ld)
+    dbias = torch.zeros(B, nq, nk).cuda()
+    ds = K.softmax_bwd(p, dev(dp), B, H, nq, nk, ld, (0, 0, 1.0), 0.125, dbias)
+    rdb = torch.zeros(B, nq, nk)
+    rds = E.softmax_bwd(f32(p), dp, B, H, nq, nk, ld, (0, 0, 1.0), 0.125, rdb)
+    assert rel_l2(ds, rds) < 6e-3 and rel_l2(dbias, rdb) < 1e-4
+    # dropout variant: probabilities kept are scaled, the mask replays in backward
+    th, sc = K.drop_params(0.1)
+    p2, pd2 = K.softmax_fwd(dev(s), dev(kmask), dev(bias), B, H, nq, nk, ld, (9, th, sc))
+    assert torch.equal(p2, p)
+    kept = pd2.cpu().float() != 0
+    big = rp > 1e-3
+    assert abs(float(kept[big].float().mean()) - 0.9) < 2e-2
+
+
+# ----------------------------------------------------------------------------------------- row utilities
+def test_embed_and_rows(K):
+    V, L, H, B = 500, 80, 768, 4
+    word, pos, typ = torch.randn(V, H), torch.randn(512, H), torch.randn(2, H)
+    ids = torch.randint(0, V, (B, L))
+    ids[0, -5:] = 0
+    z = K.embed_sum(dev(ids), dev(word), dev(pos), dev(typ[0].contiguous()))
+    assert torch.equal(z.cpu(), E.embed_sum(ids, word, pos, typ[0]))
+    dz = torch.randn(B * L, H)
+    dw, dp_, dt = torch.zeros(V, H).cuda(), torch.zeros(512, H).cuda(), torch.zeros(2, H).cuda()
+    K.embed_scatter_grad(dev(ids), dev(dz), L, 0, dw, dp_, dt[0])
+    rw, rp, rt = torch.zeros(V, H), torch.zeros(512, H), torch.zeros(2, H)
+    E.embed_scatter_grad(ids, dz, L, 0, rw, rp, rt[0])
+    assert rel_l2(dw, rw) < 1e-5 and rel_l2(dp_, rp) < 1e-5 and rel_l2(dt, rt) < 1e-5
+    assert float(dw[0].abs().max()) == 0.0
+    src = rnd(300, H)
+    idx = torch.randint(-1, 300, (1000,))
+    assert torch.equal(K.gather_rows(dev(src), dev(idx), H).cpu().float(), E.gather_rows(f32(src), idx, H))
+    out = torch.zeros(300, H).cuda()
+    g = rnd(1000, H, seed=3)
+    K.scatter_add_rows(dev(g), dev(idx), H, out)
+    assert rel_l2(out, E.scatter_add_rows(f32(g), idx, H, torch.zeros(300, H))) < 1e-5
+    a, b = rnd(640, H), rnd(640, H, seed=4)
+    table, vec = torch.randn(3, H), torch.randn(H)
+    ti = torch.randint(0, 3, (640,))
+    assert rel_l2(K.add_rows(dev(a), dev(b), dev(table), dev(ti), dev(vec)), E.add_rows(f32(a), f32(b), table, ti, vec)) < 4e-3
+    assert rel_l2(K.add_act(dev(a), dev(b)), f32(a) + f32(b)) < 4e-3
+    seg_off = torch.tensor([0, 0, 36, 38, 38, 39], dtype=torch.int32)
+    sidx = torch.randint(0, 300, (39,), dtype=torch.int32)
+    w = torch.rand(39)
+    o = K.segment_wsum(dev(src), dev(seg_off), dev(sidx), dev(w), 5, H)
+    assert rel_l2(o, E.segment_wsum(f32(src), seg_off, sidx, w, 5, H)) < 4e-3
+    d32 = torch.zeros(300, H).cuda()
+    K.segment_wsum_bwd(o, dev(seg_off), dev(sidx), dev(w), 5, H, d32)
+    assert rel_l2(d32, E.segment_wsum_bwd(f32(o), seg_off, sidx, w, 5, H, torch.zeros(300, H))) < 1e-5
+    pre = rnd(1000, H, scale=2.0, seed=5)
+    assert rel_l2(K.gelu_bwd(dev(g), dev(pre)), E.gelu_bwd(f32(g), f32(pre))) < 5e-3
+    assert rel_l2(K.relu_bwd(dev(g), dev(pre)), E.relu_bwd(f32(g), f32(pre))) < 1e-6
+    gs = torch.rand(1000)
+    x2 = dev(g.clone())
+    K.scale_rows_(x2, dev(gs), 1000, H)
+    assert rel_l2(x2, f32(g) * gs[:, None]) < 4e-3
+
+
+def test_softmax_xent(K):
+    rows, V = 37, 30522
+    ld = (V + 7) // 8 * 8
+    logits = torch.randn(rows, ld) * 3
+    labels = torch.randint(0, V, (rows,))
+    labels[3] = -1
+    loss, dl = K.softmax_xent(dev(logits), dev(labels), V, ld)
+    rl, rdl = E.softmax_xent(logits, labels, V, ld)
+    assert torch.allclose(loss.cpu(), rl, rtol=1e-5, atol=1e-5)
+    assert rel_l2(dl, rdl) < 5e-3
+    ref = torch.nn.functional.cross_entropy(logits[:, :V], labels.clamp(min=0), reduction="none")
+    assert torch.allclose(loss.cpu()[labels >= 0], ref[labels >= 0], rtol=1e-5, atol=1e-5)
+
+
+# ----------------------------------------------------------------------------------------- GEMM / attention through blocks
+def test_linear_helpers(K):
+    import bevbert_b200.blocks as Bk
+    M, Kd, N = 1000, 768, 3072
+    x, w, b = rnd(M, Kd), rnd(N, Kd, scale=0.05, seed=1), torch.randn(N) * 0.1
+    y, pre = Bk.lin_fwd(dev(x), dev(w), dev(b), act=K.ACT_GELU, want_pre=True)
+    rpre = f32(x) @ f32(w).T + b
+    assert rel_l2(pre, rpre) < 4e-3
+    assert rel_l2(y, torch.nn.functional.gelu(rpre)) < 4e-3
+    dy = rnd(M, N, seed=2)
+    dy2, w2 = rnd(M, Kd, seed=6), rnd(Kd, N, scale=0.05, seed=7)      # FFN output dense backward shape
+    dh = Bk.lin_bwd_dx(dev(dy2), dev(w2), epi_mul=K.EPI_DGELU, aux_in=pre, add_in=dev(dy))
+    assert rel_l2(dh, E.gelu_bwd(f32(dy2) @ f32(w2), f32(pre)) + f32(dy)) < 6e-3
+    dxe = Bk.lin_bwd_dx(dev(dy), dev(w))
+    assert rel_l2(dxe, f32(dy) @ f32(w)) < 4e-3
+    dw = Bk.lin_bwd_dw(dev(dy), dev(x))
+    assert rel_l2(dw, f32(dy).T @ f32(x)) < 1e-4
+    # tiny / padded shapes used by the heads and position features
+    x8, w8 = rnd(50, 16), rnd(768, 16, seed=3)
+    y8, _ = Bk.lin_fwd(dev(x8), dev(w8), None)
+    assert rel_l2(y8, f32(x8) @ f32(w8).T) < 4e-3
+    h, w1 = rnd(64, 768), rnd(8, 768, seed=4)
+    o, _ = Bk.lin_fwd(dev(h), dev(w1), None, out_f32=True)
+    assert rel_l2(o, f32(h) @ f32(w1).T) < 1e-4
+
+
+@pytest.mark.parametrize("B,nq,nk,cross", [(3, 441, 441, False), (3, 441, 80, True), (2, 20, 80, True), (5, 36, 36, False),
+                                           (2, 80, 461, True)])
+def test_attention_core(K, B, nq, nk, cross):
+    import bevbert_b200.blocks as Bk
+    H, dh = 12, 64
+    Hd = H * dh
+    if cross:
+        q = rnd(B * nq, Hd)
+        kv = rnd(B * nk, 2 * Hd, seed=1)
+        qd, kvd = dev(q), dev(kv)
+        views = (qd, Hd, kvd, 2 * Hd, kvd[:, Hd:], 2 * Hd)
+        qf, kf, vf = f32(q), f32(kv)[:, :Hd], f32(kv)[:, Hd:]
+    else:
+        qkv = rnd(B * nq, 3 * Hd)
+        qd = dev(qkv)
+        views = (qd, 3 * Hd, qd[:, Hd:], 3 * Hd, qd[:, 2 * Hd:], 3 * Hd)
+        qf, kf, vf = f32(qkv)[:, :Hd], f32(qkv)[:, Hd:2 * Hd], f32(qkv)[:, 2 * Hd:]
+    kmask = torch.zeros(B, nk)
+    kmask[0, nk - nk // 3:] = -10000.0
+    bias = torch.randn(B, nq, nk) * 0.3 if not cross else None
+    st = {}
+    ctx = Bk.attn_core_fwd(st, *views, B, H, nq, nk, dh, dev(kmask), dev(bias), (0, 0, 1.0))
+
+    def heads(t, n):
+        return t.reshape(B, n, H, dh).permute(0, 2, 1, 3)
+    qh, kh, vh = heads(qf, nq).requires_grad_(True), heads(kf, nk).requires_grad_(True), heads(vf, nk).requires_grad_(True)
+    s = qh @ kh.transpose(-1, -2) / math.sqrt(dh) + kmask[:, None, None, :]
+    if bias is not None:
+        s = s + bias[:, None]
+    ref = (torch.softmax(s, -1) @ vh).permute(0, 2, 1, 3).reshape(B * nq, Hd)
+    assert rel_l2(ctx, ref) < 8e-3
+    dctx = rnd(B * nq, Hd, seed=5)
+    ref.backward(f32(dctx))
+    if cross:
+        dq, dkv = torch.zeros_like(qd), torch.zeros_like(kvd)
+        Bk.attn_core_bwd(st, dev(dctx), *views, dq, Hd, dkv, 2 * Hd, dkv[:, Hd:], 2 * Hd)
+        gq, gk, gv = f32(dq), f32(dkv)[:, :Hd], f32(dkv)[:, Hd:]
+    else:
+        dqkv = torch.zeros_like(qd)
+        dbias = torch.zeros(B, nq, nk).cuda()
+        Bk.attn_core_bwd(st, dev(dctx), *views, dqkv, 3 * Hd, dqkv[:, Hd:], 3 * Hd, dqkv[:, 2 * Hd:], 3 * Hd, dbias)
+        gq, gk, gv = f32(dqkv)[:, :Hd], f32(dqkv)[:, Hd:2 * Hd], f32(dqkv)[:, 2 * Hd:]
+
+    def unheads(t, n):
+        return t.permute(0, 2, 1, 3).reshape(B * n, Hd)
+    assert rel_l2(gq, unheads(qh.grad, nq)) < 1.5e-2
+    assert rel_l2(gk, unheads(kh.grad, nk)) < 1.5e-2
+    assert rel_l2(gv, unheads(vh.grad, nk)) < 1.5e-2
+
+
+def test_launch_counter(K):
+    K.reset_launch_count()
+    K.cast_to_act(torch.zeros(64, device="cuda"))
+    assert K.launch_count() == 1

@@ -1,0 +1,111 @@
+"""ctypes binding of the C ABI in include/bevbert_b200.h (libbevbert_b200.so, built in-tree by
+vln-bevbert_b200/csrc/Makefile or __graft_entry__.build()).
+
+There is no fallback: if the shared library is missing or a symbol is absent, importing / calling fails
+loudly.  This is the binding a maintainer of the reference would add.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libbevbert_b200.so")
+
+c_void_p, c_int, c_i32, c_i64, c_u32, c_u64, c_float = (C.c_void_p, C.c_int, C.c_int32, C.c_int64, C.c_uint32,
+                                                         C.c_uint64, C.c_float)
+
+
+class GemmArgs(C.Structure):
+    """struct bb_gemm_args (include/bevbert_b200.h)."""
+    _fields_ = [
+        ("A", c_void_p), ("B", c_void_p), ("D", c_void_p),
+        ("M", c_i32), ("N", c_i32), ("K", c_i32),
+        ("nb1", c_i32), ("nb2", c_i32),
+        ("a_mn", c_i32), ("b_mn", c_i32),
+        ("lda", c_i64), ("a_s1", c_i64), ("a_s2", c_i64),
+        ("ldb", c_i64), ("b_s1", c_i64), ("b_s2", c_i64),
+        ("ldd", c_i64), ("d_s1", c_i64), ("d_s2", c_i64),
+        ("out_f32", c_i32), ("accumulate", c_i32), ("split_k", c_i32),
+        ("alpha", c_float),
+        ("bias", c_void_p),
+        ("act", c_i32),
+        ("aux_out", c_void_p), ("aux_in", c_void_p),
+        ("epi_mul", c_i32),
+        ("drop_seed", c_u64), ("drop_thresh", c_u32), ("drop_scale", c_float),
+        ("add_in", c_void_p),
+        ("block_n", c_i32),
+    ]
+
+
+# name -> (restype, argtypes); mirrors include/bevbert_b200.h one to one
+_SIGNATURES = {
+    "bb_last_error": (C.c_char_p, []),
+    "bb_abi_version": (c_int, []),
+    "bb_launch_count": (c_i64, []),
+    "bb_reset_launch_count": (None, []),
+    "bb_gemm_bf16": (c_int, [C.POINTER(GemmArgs), c_void_p]),
+    "bb_bev_lift_index": (c_int, [c_void_p] * 4 + [c_int] * 4 + [c_float] * 5 + [c_int, c_float, c_float, c_void_p,
+                                                                                  c_void_p, c_void_p]),
+    "bb_bev_scatter_mean_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int] + [c_void_p] * 5),
+    "bb_bev_scatter_sem_f64": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "bb_cast_f32_bf16": (c_int, [c_void_p, c_void_p, c_i64, c_u64, c_u32, c_float, c_void_p]),
+    "bb_cast_bf16_f32": (c_int, [c_void_p, c_void_p, c_i64, c_void_p]),
+    "bb_layernorm_fwd": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_float, c_i64, c_int,
+                                 c_u64, c_u32, c_float, c_u64, c_u32, c_float,
+                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "bb_layernorm_bwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_int,
+                                 c_u64, c_u32, c_float, c_u64, c_u32, c_float,
+                                 c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "bb_colsum_bf16": (c_int, [c_void_p, c_i64, c_int, c_i64, c_void_p, c_void_p]),
+    "bb_softmax_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_u64, c_u32, c_float,
+                               c_void_p, c_void_p, c_void_p]),
+    "bb_softmax_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_u64, c_u32, c_float, c_float,
+                               c_void_p, c_void_p, c_void_p]),
+    "bb_embed_sum": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_int, c_int, c_void_p, c_void_p]),
+    "bb_embed_scatter_grad": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_int, c_i64, c_void_p, c_void_p, c_void_p,
+                                      c_void_p]),
+    "bb_gather_rows_bf16": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_void_p, c_void_p]),
+    "bb_scatter_add_rows": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_void_p, c_void_p]),
+    "bb_dropout_bf16": (c_int, [c_void_p, c_void_p, c_i64, c_u64, c_u32, c_float, c_void_p]),
+    "bb_act_bwd_bf16": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_i64, c_void_p]),
+    "bb_add_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_int, c_void_p, c_void_p]),
+    "bb_scale_rows_bf16": (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_void_p]),
+    "bb_segment_wsum": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_int, c_void_p, c_void_p]),
+    "bb_segment_wsum_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_int, c_void_p, c_void_p]),
+    "bb_add_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_void_p]),
+    "bb_axpy_f32_from_bf16": (c_int, [c_void_p, c_void_p, c_i64, c_void_p]),
+    "bb_softmax_xent": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_i64, c_void_p, c_void_p, c_void_p, c_void_p]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES.keys())
+
+_lib = None
+
+
+class BevbertLibraryError(RuntimeError):
+    pass
+
+
+def load():
+    """Loads the shared library once and sets every prototype. Raises if it (or a symbol) is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise BevbertLibraryError(
+            "%s not found: build it with `make -C vln-bevbert_b200/csrc` or `python -c 'import __graft_entry__ as g; "
+            "g.build()'`. There is no CPU / PyTorch fallback for the hot path." % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name, None)
+        if fn is None:
+            raise BevbertLibraryError("symbol %s missing from %s" % (name, LIB_PATH))
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = load().bb_last_error()
+        raise BevbertLibraryError("%s failed (rc=%d): %s" % (what, rc, msg.decode() if msg else "?"))

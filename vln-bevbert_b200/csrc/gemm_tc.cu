@@ -47,6 +47,9 @@ struct GemmKParams {
   const __nv_bfloat16* aux_in;
   int epi_mul;
   const __nv_bfloat16* add_in;
+  unsigned long long drop_seed;
+  unsigned int drop_thresh;
+  float drop_scale;
 };
 
 struct TileCoord {
@@ -258,6 +261,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             for (int i = 0; i < 16; ++i) v[i] = a[i] > 0.0f ? v[i] : 0.0f;
           }
         }
+        if (p.drop_thresh != 0) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            v[i] = drop_keep(p.drop_seed, (uint64_t)(off + i), p.drop_thresh) ? v[i] * p.drop_scale : 0.0f;
+        }
         if (p.add_in != nullptr) {
           if (full && p.vec_ok) {
             __align__(16) __nv_bfloat16 h[16];
@@ -390,7 +398,7 @@ extern "C" int bb_gemm_bf16(const bb_gemm_args* a, void* stream_) {
   const int split_k_req = a->split_k > 1 ? a->split_k : 1;
   const bool atomic = a->accumulate || split_k_req > 1;
   if (atomic && !a->out_f32) return set_error("bb_gemm_bf16: accumulate / split_k need fp32 output");
-  if (atomic && (a->act || a->epi_mul || a->aux_out || a->add_in))
+  if (atomic && (a->act || a->epi_mul || a->aux_out || a->add_in || a->drop_thresh))
     return set_error("bb_gemm_bf16: accumulate / split_k cannot be combined with a non-linear epilogue");
 
   GemmKParams p;
@@ -437,6 +445,9 @@ extern "C" int bb_gemm_bf16(const bb_gemm_args* a, void* stream_) {
   p.aux_in = reinterpret_cast<const __nv_bfloat16*>(a->aux_in);
   p.epi_mul = a->epi_mul;
   p.add_in = reinterpret_cast<const __nv_bfloat16*>(a->add_in);
+  p.drop_seed = a->drop_seed;
+  p.drop_thresh = a->drop_thresh;
+  p.drop_scale = a->drop_scale;
   if (p.epi_mul && !p.aux_in) return set_error("bb_gemm_bf16: epi_mul needs aux_in");
   // vector epilogue only when every row segment of 16 outputs is 16-byte aligned (for bf16: 8 elements)
   {

@@ -102,6 +102,117 @@ __global__ void add_bf16_kernel(const bf16* __restrict__ a, const bf16* __restri
     }
   }
 }
+__global__ void dropout_bf16_kernel(const bf16* __restrict__ src, bf16* __restrict__ dst, long long n, uint64_t seed,
+                                    uint32_t thresh, float scale) {
+  const long long stride = (long long)gridDim.x * blockDim.x * 8;
+  for (long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 8; i < n; i += stride) {
+    if (i + 8 <= n) {
+      float v[8];
+      load8(src + i, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = drop_keep(seed, i + j, thresh) ? v[j] * scale : 0.f;
+      store8(dst + i, v);
+    } else {
+      for (long long j = i; j < n; ++j)
+        dst[j] = __float2bfloat16(drop_keep(seed, j, thresh) ? __bfloat162float(src[j]) * scale : 0.f);
+    }
+  }
+}
+__global__ void act_bwd_bf16_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ aux, int mode,
+                                    bf16* __restrict__ out, long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x * 8;
+  for (long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 8; i < n; i += stride) {
+    if (i + 8 <= n) {
+      float g[8], a[8];
+      load8(dy + i, g);
+      load8(aux + i, a);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] = (mode == 1) ? g[j] * dgelu_erf(a[j]) : (a[j] > 0.f ? g[j] : 0.f);
+      store8(out + i, g);
+    } else {
+      for (long long j = i; j < n; ++j) {
+        const float a = __bfloat162float(aux[j]), g = __bfloat162float(dy[j]);
+        out[j] = __float2bfloat16((mode == 1) ? g * dgelu_erf(a) : (a > 0.f ? g : 0.f));
+      }
+    }
+  }
+}
+// out = a (+ b) (+ table[idx[r]]) (+ vec)
+__global__ void add_rows_kernel(const bf16* __restrict__ a, const bf16* __restrict__ b, const float* __restrict__ table,
+                                const int64_t* __restrict__ idx, const float* __restrict__ vec, long long rows, int H,
+                                bf16* __restrict__ out) {
+  const int h8 = H / 8;
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= rows * h8) return;
+  const long long r = i / h8;
+  const int c = (i % h8) * 8;
+  float v[8];
+  load8(a + r * H + c, v);
+  if (b) {
+    float t[8];
+    load8(b + r * H + c, t);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] += t[j];
+  }
+  if (table) {
+    float t[8];
+    load8(table + idx[r] * H + c, t);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] += t[j];
+  }
+  if (vec) {
+    float t[8];
+    load8(vec + c, t);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] += t[j];
+  }
+  store8(out + r * H + c, v);
+}
+__global__ void scale_rows_bf16_kernel(bf16* __restrict__ x, const float* __restrict__ g, long long rows, long long ld) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= rows * ld) return;
+  x[i] = __float2bfloat16(__bfloat162float(x[i]) * g[i / ld]);
+}
+// one warp per segment; lanes stride over H in 8-wide chunks
+__global__ void segment_wsum_kernel(const bf16* __restrict__ src, const int32_t* __restrict__ seg_off,
+                                    const int32_t* __restrict__ idx, const float* __restrict__ w, long long nseg, int H,
+                                    bf16* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const long long s = blockIdx.x * 8LL + (threadIdx.x >> 5);
+  if (s >= nseg) return;
+  const int e0 = seg_off[s], e1 = seg_off[s + 1];
+  for (int c = lane * 8; c < H; c += 256) {
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int e = e0; e < e1; ++e) {
+      float v[8];
+      load8(src + (long long)idx[e] * H + c, v);
+      const float ww = w[e];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += ww * v[j];
+    }
+    store8(out + s * H + c, acc);
+  }
+}
+__global__ void segment_wsum_bwd_kernel(const bf16* __restrict__ dout, const int32_t* __restrict__ seg_off,
+                                        const int32_t* __restrict__ idx, const float* __restrict__ w, long long nseg,
+                                        int H, float* __restrict__ dsrc) {
+  const int lane = threadIdx.x & 31;
+  const long long s = blockIdx.x * 8LL + (threadIdx.x >> 5);
+  if (s >= nseg) return;
+  const int e0 = seg_off[s], e1 = seg_off[s + 1];
+  for (int c = lane * 8; c < H; c += 256) {
+    float g[8];
+    load8(dout + s * H + c, g);
+    for (int e = e0; e < e1; ++e) {
+      const float ww = w[e];
+      float* d = dsrc + (long long)idx[e] * H + c;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) atomicAdd(d + j, ww * g[j]);
+    }
+  }
+}
 __global__ void axpy_f32_from_bf16_kernel(const bf16* __restrict__ x, float* __restrict__ y, long long n) {
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += stride)
@@ -551,6 +662,59 @@ extern "C" int bb_add_bf16(const void* a, const void* b, void* out, int64_t n, v
   add_bf16_kernel<<<grid1d(n, 256 * 8), 256, 0, STREAM>>>((const bf16*)a, (const bf16*)b, (bf16*)out, n);
   count_launch();
   return check_launch("add_bf16_kernel");
+}
+extern "C" int bb_dropout_bf16(const void* src, void* dst, int64_t n, uint64_t seed, uint32_t thresh, float scale,
+                               void* stream) {
+  if (n <= 0) return 0;
+  if (((uintptr_t)src & 15) || ((uintptr_t)dst & 15)) return set_error("bb_dropout_bf16: pointers must be 16B aligned");
+  dropout_bf16_kernel<<<grid1d(n, 256 * 8), 256, 0, STREAM>>>((const bf16*)src, (bf16*)dst, n, seed, thresh, scale);
+  count_launch();
+  return check_launch("dropout_bf16_kernel");
+}
+extern "C" int bb_act_bwd_bf16(const void* dy, const void* aux, int mode, void* out, int64_t n, void* stream) {
+  if (n <= 0) return 0;
+  if (mode != 1 && mode != 2) return set_error("bb_act_bwd_bf16: mode must be 1 (gelu) or 2 (relu)");
+  if (((uintptr_t)dy & 15) || ((uintptr_t)aux & 15) || ((uintptr_t)out & 15))
+    return set_error("bb_act_bwd_bf16: pointers must be 16B aligned");
+  act_bwd_bf16_kernel<<<grid1d(n, 256 * 8), 256, 0, STREAM>>>((const bf16*)dy, (const bf16*)aux, mode, (bf16*)out, n);
+  count_launch();
+  return check_launch("act_bwd_bf16_kernel");
+}
+extern "C" int bb_add_rows(const void* a, const void* b, const float* table, const int64_t* idx, const float* vec,
+                           int64_t rows, int H, void* out, void* stream) {
+  if (rows <= 0) return 0;
+  if (H % 8 != 0) return set_error("bb_add_rows: H must be a multiple of 8");
+  if (table && !idx) return set_error("bb_add_rows: table needs idx");
+  const long long n = rows * (H / 8);
+  add_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, STREAM>>>((const bf16*)a, (const bf16*)b, table, idx, vec,
+                                                                   rows, H, (bf16*)out);
+  count_launch();
+  return check_launch("add_rows_kernel");
+}
+extern "C" int bb_scale_rows_bf16(void* x, const float* g, int64_t rows, int64_t ld, void* stream) {
+  if (rows <= 0) return 0;
+  const long long n = rows * ld;
+  scale_rows_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, STREAM>>>((bf16*)x, g, rows, ld);
+  count_launch();
+  return check_launch("scale_rows_bf16_kernel");
+}
+extern "C" int bb_segment_wsum(const void* src, const int32_t* seg_off, const int32_t* idx, const float* w,
+                               int64_t nseg, int H, void* out, void* stream) {
+  if (nseg <= 0) return 0;
+  if (H % 8 != 0) return set_error("bb_segment_wsum: H must be a multiple of 8");
+  segment_wsum_kernel<<<(unsigned)((nseg + 7) / 8), 256, 0, STREAM>>>((const bf16*)src, seg_off, idx, w, nseg, H,
+                                                                      (bf16*)out);
+  count_launch();
+  return check_launch("segment_wsum_kernel");
+}
+extern "C" int bb_segment_wsum_bwd(const void* dout, const int32_t* seg_off, const int32_t* idx, const float* w,
+                                   int64_t nseg, int H, float* dsrc_f32, void* stream) {
+  if (nseg <= 0) return 0;
+  if (H % 8 != 0) return set_error("bb_segment_wsum_bwd: H must be a multiple of 8");
+  segment_wsum_bwd_kernel<<<(unsigned)((nseg + 7) / 8), 256, 0, STREAM>>>((const bf16*)dout, seg_off, idx, w, nseg, H,
+                                                                          dsrc_f32);
+  count_launch();
+  return check_launch("segment_wsum_bwd_kernel");
 }
 extern "C" int bb_axpy_f32_from_bf16(const void* x, float* y, int64_t n, void* stream) {
   if (n <= 0) return 0;

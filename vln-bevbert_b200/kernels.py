@@ -1,0 +1,332 @@
+"""Tensor-level wrappers: one thin Python function per C-ABI entry point (include/bevbert_b200.h).
+
+Each wrapper only extracts device pointers / sizes from torch tensors, passes torch's current CUDA stream and
+raises on a non-zero status.  There is no arithmetic here and no fallback: without the CUDA library these
+functions raise.  (tests/emu_kernels.py replaces this module's functions with torch restatements to
+exercise the host-side block logic on CPU; that emulation is test infrastructure, never shipped.)
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+
+ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
+EPI_NONE, EPI_DGELU, EPI_DRELU = 0, 1, 2
+BF16 = torch.bfloat16
+
+
+def act_dtype():
+    """dtype of activations between kernels (bf16 in the product)."""
+    return BF16
+
+
+def _p(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _req(t, dtype, name):
+    if t.dtype != dtype:
+        raise TypeError("%s must be %s, got %s" % (name, dtype, t.dtype))
+    if not t.is_cuda:
+        raise RuntimeError("%s must be a CUDA tensor (the hot path has no CPU implementation)" % name)
+
+
+def drop_params(p: float):
+    """(thresh, scale) of the counter-based dropout for probability p."""
+    if p <= 0.0:
+        return 0, 1.0
+    return min(int(p * 4294967296.0), 4294967295), 1.0 / (1.0 - p)
+
+
+def launch_count() -> int:
+    return int(_lib.load().bb_launch_count())
+
+
+def reset_launch_count():
+    _lib.load().bb_reset_launch_count()
+
+
+# ---------------------------------------------------------------------------------------------- GEMM
+def gemm(a, b, out, M, N, K, lda, ldb, ldd, a_mn=False, b_mn=False, nb1=1, nb2=1, a_s=(0, 0), b_s=(0, 0),
+         d_s=(0, 0), alpha=1.0, bias=None, act=ACT_NONE, aux_out=None, aux_in=None, epi_mul=EPI_NONE, add_in=None,
+         accumulate=False, split_k=1, drop=(0, 0, 1.0), block_n=0):
+    """out = epi(alpha * A @ B^T) on tcgen05; a/b/out are base tensors (pointer = data_ptr()), strides in
+    elements.  out dtype bf16 or f32 decides the output type.  drop = (seed, thresh, scale)."""
+    lib = _lib.load()
+    _req(a, BF16, "a")
+    _req(b, BF16, "b")
+    g = _lib.GemmArgs()
+    g.A, g.B, g.D = a.data_ptr(), b.data_ptr(), out.data_ptr()
+    g.M, g.N, g.K = M, N, K
+    g.nb1, g.nb2 = nb1, nb2
+    g.a_mn, g.b_mn = int(a_mn), int(b_mn)
+    g.lda, g.a_s1, g.a_s2 = lda, a_s[0], a_s[1]
+    g.ldb, g.b_s1, g.b_s2 = ldb, b_s[0], b_s[1]
+    g.ldd, g.d_s1, g.d_s2 = ldd, d_s[0], d_s[1]
+    if out.dtype == torch.float32:
+        g.out_f32 = 1
+    elif out.dtype == BF16:
+        g.out_f32 = 0
+    else:
+        raise TypeError("gemm output must be bf16 or f32")
+    g.accumulate, g.split_k = int(accumulate), split_k
+    g.alpha = alpha
+    g.bias = _p(bias)
+    g.act = act
+    g.aux_out, g.aux_in, g.epi_mul = _p(aux_out), _p(aux_in), epi_mul
+    g.drop_seed, g.drop_thresh, g.drop_scale = drop
+    g.add_in = _p(add_in)
+    g.block_n = block_n
+    _lib.check(lib.bb_gemm_bf16(C.byref(g), _stream()), "bb_gemm_bf16")
+    return out
+
+
+# ---------------------------------------------------------------------------------------------- BEV
+def bev_lift_index(depths, T_c2w, S_w2c, T_w2c, map_dim, map_res, depth_scale=10.0, fx=7.0, fy=7.0, cx=7.0, cy=7.0,
+                   y_clip=0.5, want_pc=False):
+    lib = _lib.load()
+    for t, n in ((depths, "depths"), (T_c2w, "T_c2w"), (S_w2c, "S_w2c"), (T_w2c, "T_w2c")):
+        _req(t, torch.float32, n)
+    B, V = depths.shape[0], depths.shape[1]
+    Hf, Wf = depths.shape[-2], depths.shape[-1]
+    P = V * Hf * Wf
+    idx = torch.empty(B, P, dtype=torch.int32, device=depths.device)
+    pc = torch.empty(B, P, 3, dtype=torch.float32, device=depths.device) if want_pc else None
+    _lib.check(lib.bb_bev_lift_index(depths.contiguous().data_ptr(), T_c2w.contiguous().data_ptr(),
+                                     S_w2c.contiguous().data_ptr(), T_w2c.contiguous().data_ptr(), B, V, Hf, Wf,
+                                     depth_scale, fx, fy, cx, cy, map_dim, map_res, y_clip, idx.data_ptr(), _p(pc),
+                                     _stream()), "bb_bev_lift_index")
+    return idx, pc
+
+
+def bev_scatter_mean(feats, cell_idx, ncell, want_f32=True, want_bf16=True):
+    """feats f32 (B,P,C) -> (bev_f32 | None, bev_bf16 | None, ob_mask bool (B,ncell), counts int32)."""
+    lib = _lib.load()
+    _req(feats, torch.float32, "feats")
+    B, P, Cc = feats.shape
+    dev = feats.device
+    o32 = torch.empty(B, ncell, Cc, dtype=torch.float32, device=dev) if want_f32 else None
+    o16 = torch.empty(B, ncell, Cc, dtype=BF16, device=dev) if want_bf16 else None
+    ob = torch.empty(B, ncell, dtype=torch.uint8, device=dev)
+    cnt = torch.empty(B, ncell, dtype=torch.int32, device=dev)
+    _lib.check(lib.bb_bev_scatter_mean_f32(feats.contiguous().data_ptr(), cell_idx.data_ptr(), B, P, Cc, ncell,
+                                           _p(o32), _p(o16), ob.data_ptr(), cnt.data_ptr(), _stream()),
+               "bb_bev_scatter_mean_f32")
+    return o32, o16, ob.bool(), cnt
+
+
+def bev_scatter_sem(sems, cell_idx, ncell):
+    lib = _lib.load()
+    _req(sems, torch.float64, "sems")
+    B, P, S = sems.shape
+    out = torch.empty(B, ncell, S, dtype=torch.float64, device=sems.device)
+    m = torch.empty(B, ncell, dtype=torch.uint8, device=sems.device)
+    _lib.check(lib.bb_bev_scatter_sem_f64(sems.contiguous().data_ptr(), cell_idx.data_ptr(), B, P, S, ncell,
+                                          out.data_ptr(), m.data_ptr(), _stream()), "bb_bev_scatter_sem_f64")
+    return out, m.bool()
+
+
+# ---------------------------------------------------------------------------------------------- row kernels
+def cast_to_act(src, drop=(0, 0, 1.0), out=None):
+    """f32 -> activation dtype (bf16), optional inverted dropout. drop = (seed, thresh, scale)."""
+    lib = _lib.load()
+    _req(src, torch.float32, "src")
+    src = src.contiguous()
+    if out is None:
+        out = torch.empty(src.shape, dtype=BF16, device=src.device)
+    _lib.check(lib.bb_cast_f32_bf16(src.data_ptr(), out.data_ptr(), src.numel(), drop[0], drop[1], drop[2],
+                                    _stream()), "bb_cast_f32_bf16")
+    return out
+
+
+def cast_to_f32(src):
+    lib = _lib.load()
+    _req(src, BF16, "src")
+    src = src.contiguous()
+    out = torch.empty(src.shape, dtype=torch.float32, device=src.device)
+    _lib.check(lib.bb_cast_bf16_f32(src.data_ptr(), out.data_ptr(), src.numel(), _stream()), "bb_cast_bf16_f32")
+    return out
+
+
+def dropout_act(src, drop, out=None):
+    lib = _lib.load()
+    _req(src, BF16, "src")
+    if out is None:
+        out = torch.empty_like(src)
+    _lib.check(lib.bb_dropout_bf16(src.data_ptr(), out.data_ptr(), src.numel(), drop[0], drop[1], drop[2], _stream()),
+               "bb_dropout_bf16")
+    return out
+
+
+def layernorm_fwd(x, residual, gamma, beta, eps, drop_in=(0, 0, 1.0), drop_out=(0, 0, 1.0), want_f32=False):
+    """x (rows,H) bf16|f32, residual bf16|None -> (y bf16, y_f32|None, mean, rstd)."""
+    lib = _lib.load()
+    rows, H = x.shape
+    dev = x.device
+    y = torch.empty(rows, H, dtype=BF16, device=dev)
+    y32 = torch.empty(rows, H, dtype=torch.float32, device=dev) if want_f32 else None
+    mean = torch.empty(rows, dtype=torch.float32, device=dev)
+    rstd = torch.empty(rows, dtype=torch.float32, device=dev)
+    _lib.check(lib.bb_layernorm_fwd(x.data_ptr(), int(x.dtype == torch.float32), _p(residual), gamma.data_ptr(),
+                                    beta.data_ptr(), eps, rows, H, drop_in[0], drop_in[1], drop_in[2], drop_out[0],
+                                    drop_out[1], drop_out[2], y.data_ptr(), _p(y32), mean.data_ptr(), rstd.data_ptr(),
+                                    _stream()), "bb_layernorm_fwd")
+    return y, y32, mean, rstd
+
+
+def layernorm_bwd(dy, x, residual, gamma, mean, rstd, drop_in=(0, 0, 1.0), drop_out=(0, 0, 1.0), want_dx=True,
+                  want_dres=False, dx_f32=False, dgamma=None, dbeta=None):
+    """-> (dx | None, dres | None); dgamma/dbeta f32 [H] are accumulated into."""
+    lib = _lib.load()
+    rows, H = x.shape
+    dev = x.device
+    dx = torch.empty(rows, H, dtype=torch.float32 if dx_f32 else BF16, device=dev) if want_dx else None
+    dres = torch.empty(rows, H, dtype=BF16, device=dev) if want_dres else None
+    _lib.check(lib.bb_layernorm_bwd(dy.data_ptr(), int(dy.dtype == torch.float32), x.data_ptr(),
+                                    int(x.dtype == torch.float32), _p(residual), gamma.data_ptr(), mean.data_ptr(),
+                                    rstd.data_ptr(), rows, H, drop_in[0], drop_in[1], drop_in[2], drop_out[0],
+                                    drop_out[1], drop_out[2], _p(dx), int(dx_f32), _p(dres), _p(dgamma), _p(dbeta),
+                                    _stream()), "bb_layernorm_bwd")
+    return dx, dres
+
+
+def colsum(x, N, out=None):
+    """column sums of a bf16 (rows, N) row-major matrix -> f32 [N] (accumulated into `out` if given)."""
+    lib = _lib.load()
+    _req(x, BF16, "x")
+    rows = x.numel() // N
+    if out is None:
+        out = torch.zeros(N, dtype=torch.float32, device=x.device)
+    _lib.check(lib.bb_colsum_bf16(x.data_ptr(), rows, N, N, out.data_ptr(), _stream()), "bb_colsum_bf16")
+    return out
+
+
+def softmax_fwd(scores, kmask, bias, nbatch, H, nq, nk, ld, drop=(0, 0, 1.0)):
+    lib = _lib.load()
+    dev = scores.device
+    probs = torch.empty(nbatch, H, nq, ld, dtype=BF16, device=dev)
+    pd = torch.empty(nbatch, H, nq, ld, dtype=BF16, device=dev) if drop[1] else None
+    _lib.check(lib.bb_softmax_fwd(scores.data_ptr(), _p(kmask), _p(bias), nbatch, H, nq, nk, ld, drop[0], drop[1],
+                                  drop[2], probs.data_ptr(), _p(pd), _stream()), "bb_softmax_fwd")
+    return probs, (pd if pd is not None else probs)
+
+
+def softmax_bwd(probs, dprobs, nbatch, H, nq, nk, ld, drop, out_scale, dbias=None):
+    lib = _lib.load()
+    ds = torch.empty(nbatch, H, nq, ld, dtype=BF16, device=probs.device)
+    _lib.check(lib.bb_softmax_bwd(probs.data_ptr(), dprobs.data_ptr(), nbatch, H, nq, nk, ld, drop[0], drop[1],
+                                  drop[2], out_scale, ds.data_ptr(), _p(dbias), _stream()), "bb_softmax_bwd")
+    return ds
+
+
+def embed_sum(ids, word, pos, type0):
+    lib = _lib.load()
+    Bn, L = ids.shape
+    H = word.shape[1]
+    out = torch.empty(Bn * L, H, dtype=torch.float32, device=word.device)
+    _lib.check(lib.bb_embed_sum(ids.contiguous().data_ptr(), word.data_ptr(), pos.data_ptr(), type0.data_ptr(),
+                                Bn * L, L, H, out.data_ptr(), _stream()), "bb_embed_sum")
+    return out
+
+
+def embed_scatter_grad(ids, dz, L, padding_idx, dword, dpos, dtype0):
+    lib = _lib.load()
+    ntok, H = dz.shape
+    _lib.check(lib.bb_embed_scatter_grad(ids.contiguous().data_ptr(), dz.data_ptr(), ntok, L, H, padding_idx,
+                                         _p(dword), _p(dpos), _p(dtype0), _stream()), "bb_embed_scatter_grad")
+
+
+def gather_rows(src, idx, H):
+    """out[r] = src[idx[r]] (bf16 rows of width H); idx int64, negative -> zero row."""
+    lib = _lib.load()
+    out = torch.empty(idx.numel(), H, dtype=BF16, device=src.device)
+    _lib.check(lib.bb_gather_rows_bf16(src.data_ptr(), idx.data_ptr(), idx.numel(), H, out.data_ptr(), _stream()),
+               "bb_gather_rows_bf16")
+    return out
+
+
+def scatter_add_rows(src, idx, H, out_f32):
+    """out_f32[idx[r]] += src[r]."""
+    lib = _lib.load()
+    _lib.check(lib.bb_scatter_add_rows(src.data_ptr(), idx.data_ptr(), idx.numel(), H, out_f32.data_ptr(), _stream()),
+               "bb_scatter_add_rows")
+    return out_f32
+
+
+def _act_bwd(dy, aux, mode):
+    lib = _lib.load()
+    out = torch.empty_like(dy)
+    _lib.check(lib.bb_act_bwd_bf16(dy.data_ptr(), aux.data_ptr(), mode, out.data_ptr(), dy.numel(), _stream()),
+               "bb_act_bwd_bf16")
+    return out
+
+
+def gelu_bwd(dy, pre):
+    """dy * gelu'(pre) (exact erf form, vilmodel.py:31-37)."""
+    return _act_bwd(dy, pre, 1)
+
+
+def relu_bwd(dy, post):
+    """dy * (post > 0)."""
+    return _act_bwd(dy, post, 2)
+
+
+def add_rows(a, b=None, table=None, idx=None, vec=None):
+    """a (+ b) (+ table[idx]) (+ vec) over bf16 (rows,H)."""
+    lib = _lib.load()
+    rows, H = a.shape
+    out = torch.empty(rows, H, dtype=BF16, device=a.device)
+    _lib.check(lib.bb_add_rows(a.data_ptr(), _p(b), _p(table), _p(idx), _p(vec), rows, H, out.data_ptr(), _stream()),
+               "bb_add_rows")
+    return out
+
+
+def scale_rows_(x, g, rows, ld):
+    lib = _lib.load()
+    _lib.check(lib.bb_scale_rows_bf16(x.data_ptr(), g.data_ptr(), rows, ld, _stream()), "bb_scale_rows_bf16")
+    return x
+
+
+def segment_wsum(src, seg_off, idx, w, nseg, H):
+    lib = _lib.load()
+    out = torch.empty(nseg, H, dtype=BF16, device=src.device)
+    _lib.check(lib.bb_segment_wsum(src.data_ptr(), seg_off.data_ptr(), idx.data_ptr(), w.data_ptr(), nseg, H,
+                                   out.data_ptr(), _stream()), "bb_segment_wsum")
+    return out
+
+
+def segment_wsum_bwd(dout, seg_off, idx, w, nseg, H, dsrc_f32):
+    lib = _lib.load()
+    _lib.check(lib.bb_segment_wsum_bwd(dout.data_ptr(), seg_off.data_ptr(), idx.data_ptr(), w.data_ptr(), nseg, H,
+                                       dsrc_f32.data_ptr(), _stream()), "bb_segment_wsum_bwd")
+    return dsrc_f32
+
+
+def add_act(a, b):
+    lib = _lib.load()
+    out = torch.empty_like(a)
+    _lib.check(lib.bb_add_bf16(a.data_ptr(), b.data_ptr(), out.data_ptr(), a.numel(), _stream()), "bb_add_bf16")
+    return out
+
+
+def axpy_f32_from_act(x, y):
+    """y (f32) += x (bf16)."""
+    lib = _lib.load()
+    _lib.check(lib.bb_axpy_f32_from_bf16(x.data_ptr(), y.data_ptr(), x.numel(), _stream()), "bb_axpy_f32_from_bf16")
+    return y
+
+
+def softmax_xent(logits, labels, V, ld, want_grad=True):
+    """logits f32 (rows, ld) -> (loss f32 (rows,), dlogits bf16 (rows, ld) | None) with dlogits = softmax - onehot."""
+    lib = _lib.load()
+    rows = logits.shape[0]
+    loss = torch.empty(rows, dtype=torch.float32, device=logits.device)
+    dl = torch.empty(rows, ld, dtype=BF16, device=logits.device) if want_grad else None
+    _lib.check(lib.bb_softmax_xent(logits.data_ptr(), labels.data_ptr(), rows, V, ld, loss.data_ptr(), 0, _p(dl),
+                                   _stream()), "bb_softmax_xent")
+    return loss, dl

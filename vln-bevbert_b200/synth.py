@@ -339,3 +339,25 @@ def batch_to(batch: dict, device, non_blocking: bool = False) -> dict:
 def clone_batch(batch: dict) -> dict:
     """Shallow copy with cloned tensors; forward() pops / adds keys (pretrain_cmt.py:115-165)."""
     return {k: (v.clone() if torch.is_tensor(v) else v) for k, v in batch.items()}
+
+
+def det_init_(model, seed: int = 0, std: float = 0.02):
+    """Deterministic, machine-independent parameter init for tests / benchmarks: every tensor is filled from the
+    counter-based generator (uniform with the given std; LayerNorm weights around 1).  Tied parameters are
+    filled once.  Returns the model."""
+    ln_w = set()
+    for m in model.modules():
+        if isinstance(m, torch.nn.LayerNorm):
+            ln_w.add(id(m.weight))
+    a = std * math.sqrt(3.0)
+    seen = set()
+    with torch.no_grad():
+        for i, (name, p) in enumerate(sorted(model.named_parameters(), key=lambda kv: kv[0])):
+            if id(p) in seen:
+                continue
+            seen.add(id(p))
+            v = det_uniform(tuple(p.shape), seed, 1000 + i, -a, a)
+            if id(p) in ln_w:
+                v = v + 1.0
+            p.copy_(v.to(p.device))
+    return model
