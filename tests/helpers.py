@@ -39,3 +39,20 @@ def grad_report(named_grads, ref_grads, floor_frac=1e-4):
         if e > worst:
             worst, worst_name = e, n
     return worst, worst_name
+
+
+def grad_errors(named_grads, ref_grads, floor_frac=1e-2):
+    """per-parameter relative errors (same definition as grad_report) + the global relative L2 error over all
+    gradients concatenated."""
+    top = max(float(g.norm()) for g in ref_grads.values() if g is not None)
+    errs, num, den = {}, 0.0, 0.0
+    for n, g in named_grads.items():
+        r = ref_grads.get(n)
+        if r is None and g is None:
+            continue
+        assert r is not None and g is not None, "gradient presence differs for %s" % n
+        d = float((g.detach().float().cpu() - r.detach().float().cpu()).norm())
+        errs[n] = d / max(float(r.norm()), floor_frac * top)
+        num += d * d
+        den += float(r.norm()) ** 2
+    return errs, (num / max(den, 1e-60)) ** 0.5

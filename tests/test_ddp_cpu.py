@@ -1,0 +1,57 @@
+"""N > 1 path on CPU (gloo, world_size 2): the model under torch DistributedDataParallel
+(find_unused_parameters=True, as pretrain_src/utils/misc.py:70) gives, after the gradient all-reduce, the
+gradients of a single process on the concatenated batch.  Kernels are emulated (tests/emu_kernels.py)."""
+import os
+import socket
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _worker(rank, world, port, task, ret):
+    sys.path.insert(0, os.path.dirname(HERE))
+    sys.path.insert(0, HERE)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.set_num_threads(2)
+    import emu_kernels
+    emu_kernels.install()
+    from bevbert_b200 import synth
+    from bevbert_b200.model.pretrain_cmt import GlocalTextPathCMTPreTraining
+    from helpers import small_config, small_synth
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    cfg = small_config()
+    full = synth.make_batch(small_synth(batch_size=4), seed=9, task=task)
+    shard = synth.split_batch(full, world)[rank]
+    model = synth.det_init_(GlocalTextPathCMTPreTraining(cfg), seed=3).train()
+    ddp = torch.nn.parallel.DistributedDataParallel(model, find_unused_parameters=True)
+    ddp(shard, task).mean().backward()
+    grads = {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None}
+    if rank == 0:
+        single = synth.det_init_(GlocalTextPathCMTPreTraining(cfg), seed=3).train()
+        single(full, task).mean().backward()
+        ref = {n: p.grad for n, p in single.named_parameters() if p.grad is not None}
+        top = max(float(g.norm()) for g in ref.values())
+        worst = 0.0
+        assert set(ref) == set(grads), set(ref) ^ set(grads)
+        for n, g in ref.items():
+            worst = max(worst, float((grads[n] - g).norm()) / max(float(g.norm()), 1e-4 * top))
+        ret["worst"] = worst
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("task", ["sap", "mlm"])
+def test_ddp_gradients_equal_single_process(task):
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(2, port, task, ret), nprocs=2, join=True)
+    assert ret["worst"] < 1e-3, ret["worst"]

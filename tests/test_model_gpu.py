@@ -15,22 +15,46 @@ from oracle import bevbert_ref as R
 pytestmark = pytest.mark.gpu
 
 
-def _compare(task, cfg, scfg, seed=7, loss_tol=1e-2, grad_tol=3e-2):
+def _oracle_grads(sd, b, task, cfg, autocast=False):
+    for v in sd.values():
+        v.grad = None
+    if autocast:   # the reference algorithm under PyTorch bf16 autocast: the precision class of our kernels
+        with torch.autocast("cpu", dtype=torch.bfloat16):
+            out = R.forward(sd, synth.clone_batch(b), task, R.OracleConfig(cfg))
+    else:
+        out = R.forward(sd, synth.clone_batch(b), task, R.OracleConfig(cfg))
+    out.float().mean().backward()
+    return out.detach().float(), {n: v.grad.clone() for n, v in sd.items() if v.grad is not None}
+
+
+def _compare(task, cfg, scfg, seed=7, loss_tol=1e-2, global_grad_tol=1e-2, grad_tol=3e-2):
+    """Losses: relative L2 <= 1e-2 (north_star bf16 tolerance).  Gradients: relative L2 over all parameters
+    <= 1e-2; per parameter <= grad_tol, or -- for ill-conditioned gradients (softmax-CE terms that cancel
+    across near-identical tokens at random init) -- no worse than 3x what the reference algorithm itself loses
+    under PyTorch bf16 autocast on the same weights and batch."""
     model = synth.det_init_(GlocalTextPathCMTPreTraining(cfg), seed=3).cuda().train()
     sd = {k: v.detach().float().cpu().clone().requires_grad_(True) for k, v in model.state_dict().items()}
     b = synth.make_batch(scfg, seed=seed, task=task)
     out = model(synth.batch_to(b, "cuda"), task, compute_loss=True)
     out.mean().backward()
-    ref = R.forward(sd, synth.clone_batch(b), task, R.OracleConfig(cfg))
-    ref.mean().backward()
+    ref, rg = _oracle_grads(sd, b, task, cfg)
+    ac_out, ag = _oracle_grads(sd, b, task, cfg, autocast=True)
     assert out.shape == ref.shape
-    le = rel_l2(out, ref)
-    worst, name = grad_report({n: p.grad for n, p in model.named_parameters()},
-                              {n: sd[n].grad for n, _ in model.named_parameters()}, floor_frac=1e-2)
-    print("task=%s loss rel-L2=%.3e worst grad rel err=%.3e (%s)" % (task, le, worst, name))
+    le, le_ac = rel_l2(out, ref), rel_l2(ac_out, ref)
+    names = [n for n, _ in model.named_parameters()]
+    mine = {n: p.grad for n, p in model.named_parameters()}
+    errs, glob = grad_errors(mine, {n: rg.get(n) for n in names})
+    errs_ac, glob_ac = grad_errors({n: ag.get(n) for n in names}, {n: rg.get(n) for n in names})
+    worst = sorted(errs.items(), key=lambda kv: -kv[1])[:4]
+    print("task=%s loss rel-L2 ours %.3e (bf16-autocast oracle %.3e) | all-grads rel-L2 ours %.3e (autocast %.3e)" % (
+        task, le, le_ac, glob, glob_ac))
+    for n, e in worst:
+        print("    %-75s ours %.3e autocast %.3e |g_ref| %.3e" % (n, e, errs_ac[n], float(rg[n].norm())))
     assert le < loss_tol, le
-    assert worst < grad_tol, (worst, name)
-    return le, worst
+    assert glob < global_grad_tol, glob
+    bad = {n: (e, errs_ac[n]) for n, e in errs.items() if e > max(grad_tol, 3.0 * errs_ac[n])}
+    assert not bad, bad
+    return le, glob
 
 
 @pytest.mark.parametrize("task", ["mlm", "sap", "masksem"])
@@ -49,7 +73,7 @@ def test_baseline_config1_full_depth(task):
     """BASELINE.json configs[0]: B=2, 80 tokens, 36 views x 768, 11x11 BEV, 8 topo nodes, full 9/2/4/4 layers."""
     cfg = make_config(bev_dim=11, bev_res=1.0, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0,
                       feat_dropout=0.0)
-    _compare(task, cfg, small_synth(), grad_tol=5e-2)
+    _compare(task, cfg, small_synth())
 
 
 def test_bev_inputs_exact_and_logits():

@@ -361,3 +361,29 @@ def det_init_(model, seed: int = 0, std: float = 0.02):
                 v = v + 1.0
             p.copy_(v.to(p.device))
     return model
+
+
+_PANO_KEYS = ("traj_view_img_fts", "traj_obj_img_fts", "traj_vp_obj_lens", "traj_loc_fts", "traj_nav_types",
+              "traj_vp_view_lens")
+
+
+def split_batch(batch: dict, parts: int):
+    """Splits a collated batch into `parts` equal per-sample shards (what DistributedSampler would give each
+    rank): per-sample tensors / lists are sliced on dim 0, per-panorama tensors by `traj_step_lens`."""
+    B = len(batch["traj_step_lens"])
+    assert B % parts == 0
+    n = B // parts
+    pano_off = [0]
+    for s in batch["traj_step_lens"]:
+        pano_off.append(pano_off[-1] + s)
+    out = []
+    for r in range(parts):
+        lo, hi = r * n, (r + 1) * n
+        sub = {}
+        for k, v in batch.items():
+            if k in _PANO_KEYS:
+                sub[k] = v[pano_off[lo]:pano_off[hi]]
+            else:
+                sub[k] = v[lo:hi]
+        out.append(sub)
+    return out
