@@ -482,3 +482,42 @@ class OracleConfig:
         self.bev_res = bev_res if bev_res is not None else getattr(config, "bev_res", 0.5)
         self.drop_p = drop_p
         self.feat_drop_p = feat_drop_p
+
+
+# ----------------------------------------------------------------------------- navigation-side API (agents)
+def _nav_sd(sd):
+    """GlocalTextPathNavCMT keeps the encoder at the top level (no `bert.` prefix); map to the names above."""
+    heads = ("global_sap_head", "local_sap_head", "sap_fuse_linear", "og_head")
+    return {(k if k.startswith(heads) else "bert." + k): v for k, v in sd.items()}
+
+
+def nav_forward(sd, mode, batch, cfg):
+    """GlocalTextPathNavCMT.forward(mode, batch), map_nav_src/models/vilmodel.py:744-912."""
+    sd = _nav_sd(sd)
+    if mode == "language":  # forward_text :744-748
+        return language_encoder(sd, text_embeddings(sd, batch["txt_ids"], cfg), batch["txt_masks"], cfg)
+    if mode == "panorama":  # forward_panorama_per_step :750-801
+        b = {"traj_view_img_fts": batch["view_img_fts"], "traj_obj_img_fts": batch.get("obj_img_fts"),
+             "traj_loc_fts": batch["loc_fts"], "traj_nav_types": batch["nav_types"],
+             "traj_vp_view_lens": batch["view_lens"], "traj_vp_obj_lens": batch.get("obj_lens"),
+             "traj_step_lens": [batch["view_img_fts"].shape[0]]}
+        (emb,), (lens,) = image_embeddings(sd, b, cfg)
+        return emb, seq_mask(lens, emb.shape[1])
+    if mode != "navigation":
+        raise NotImplementedError(mode)
+    # forward_navigation_per_step :803-887
+    b = batch
+    p = "bert.global_encoder"
+    g = b["gmap_img_embeds"] + sd[p + ".gmap_step_embeddings.weight"][b["gmap_step_ids"]] + \
+        _ln(sd, p + ".gmap_pos_embeddings.1", _lin(sd, p + ".gmap_pos_embeddings.0", b["gmap_pos_fts"]), 1e-12)
+    gmap = crossmodal_encoder(sd, p + ".encoder", b["txt_embeds"], b["txt_masks"], g, b["gmap_masks"],
+                              graph_sprels(sd, b), cfg)
+    bev, obj = _local(sd, b, b["txt_embeds"], b["txt_masks"], b.get("obj_embeds"), b.get("obj_masks"), cfg)
+    sb = {"gmap_visited_masks": b["gmap_visited_masks"], "gmap_lens": b["gmap_masks"].sum(1), "bev_cand_idxs": b["bev_cand_idxs"],
+          "bev_nav_masks": b["bev_nav_masks"], "gmap_vpids": b["gmap_vpids"],
+          "traj_cand_vpids": [[c[1:]] for c in b["bev_cand_vpids"]]}
+    gl, ll, fl = sap_logits(sd, sb, cfg, gmap, bev)
+    ol = None
+    if obj is not None:
+        ol = _head(sd, "og_head", obj).squeeze(2).masked_fill(~b["obj_masks"], float("-inf"))
+    return {"gmap_embeds": gmap, "global_logits": gl, "local_logits": ll, "fused_logits": fl, "obj_logits": ol}

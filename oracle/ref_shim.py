@@ -80,3 +80,16 @@ def build_reference_model(config, state_dict=None):
         assert not missing and not unexpected, (missing, unexpected)
         model.tie_weights()
     return model
+
+
+def load_nav_module():
+    """map_nav_src/models/vilmodel.py (GlocalTextPathNavCMT) of the unmodified reference."""
+    if not available():
+        raise RuntimeError("reference tree not found at %s" % REF_ROOT)
+    sys.dont_write_bytecode = True
+    src = os.path.join(REF_ROOT, "map_nav_src")
+    if src not in sys.path:
+        sys.path.insert(0, src)
+    nav = importlib.import_module("models.vilmodel")
+    nav.BertPreTrainedModel.init_weights = lambda self: None
+    return nav

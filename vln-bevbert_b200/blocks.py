@@ -645,6 +645,34 @@ class CastImpl:
         return [None], []
 
 
+class ToActImpl:
+    """fp32 -> activation dtype at an API boundary, differentiable (gradient cast back to fp32)."""
+
+    def fwd(self, st, inputs, p):
+        return K.cast_to_act(inputs[0])
+
+    def bwd(self, st, gouts, p):
+        return [K.cast_to_f32(gouts[0].contiguous())], []
+
+
+class ToF32Impl:
+    """activation dtype -> fp32 at an API boundary, differentiable."""
+
+    def fwd(self, st, inputs, p):
+        return K.cast_to_f32(inputs[0])
+
+    def bwd(self, st, gouts, p):
+        return [K.cast_to_act(gouts[0].contiguous().float())], []
+
+
+def to_act(x):
+    return run_block(ToActImpl(), [x], []) if x.dtype == torch.float32 else x
+
+
+def to_f32(x):
+    return run_block(ToF32Impl(), [x], []) if x.dtype != torch.float32 else x
+
+
 # =============================================================================================== autograd glue
 class _BlockFn(torch.autograd.Function):
     @staticmethod
