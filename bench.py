@@ -28,6 +28,29 @@ FLOPS_PER_SAMPLE_FWD_BWD = 130e9               # 5:5:1 mix, 43.4
 ATTN_GEMM_FLOPS_SAP_FWD = 23.1e9               # attention-GEMM subset of one SAP forward
 
 
+def host_cores():
+    """CPU cores this process may actually use: scheduler affinity capped by the cgroup CPU quota
+    (os.cpu_count() reports the whole host inside a container and oversubscribes the oracle's thread pool)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = open(path).read().split()
+            if path.endswith("cpu.max"):
+                if txt[0] != "max":
+                    n = min(n, max(1, int(float(txt[0]) / float(txt[1]) + 0.5)))
+            else:
+                q = int(txt[0])
+                per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+                if q > 0:
+                    n = min(n, max(1, int(q / per + 0.5)))
+        except Exception:
+            pass
+    return max(1, min(n, int(os.environ.get("BEVBERT_CPU_THREADS", "64"))))
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -92,7 +115,7 @@ def run_reference(args, rank):
     from bevbert_b200 import synth
     from bevbert_b200.model.pretrain_cmt import GlocalTextPathCMTPreTraining
     from oracle import bevbert_ref as R
-    cores = os.cpu_count() or 1
+    cores = host_cores()
     torch.set_num_threads(cores)
     cfg = full_config()
     model = synth.det_init_(GlocalTextPathCMTPreTraining(cfg), seed=3)
@@ -246,7 +269,8 @@ def run_ours(args, rank, world, local_rank):
             s.record()
             r = real_gemm(a, b, out, M, N, Kd, *a_, **kw)
             e.record()
-            rec.append((2.0 * M * N * Kd * kw.get("nb1", 1) * kw.get("nb2", 1), s, e))
+            rec.append((2.0 * M * N * Kd * kw.get("nb1", 1) * kw.get("nb2", 1), s, e,
+                        (M, N, Kd, kw.get("nb1", 1) * kw.get("nb2", 1), int(kw.get("a_mn", False)), int(kw.get("b_mn", False)))))
             return r
         K.gemm = timed_gemm
         try:
@@ -261,6 +285,18 @@ def run_ours(args, rank, world, local_rank):
         tms = sum(r[1].elapsed_time(r[2]) for r in rec)
         achieved = flops / (tms * 1e-3) / 1e12
         peak = peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"]
+        by_shape = {}
+        for r in rec:
+            d = by_shape.setdefault(r[3], [0, 0.0, 0.0])
+            d[0] += 1
+            d[1] += r[1].elapsed_time(r[2])
+            d[2] += r[0]
+        top = sorted(by_shape.items(), key=lambda kv: -kv[1][1])[:14]
+        shape_rows = [{"MNKb_amn_bmn": list(k), "launches": v[0], "ms": round(v[1], 3),
+                       "tflops": round(v[2] / (v[1] * 1e-3) / 1e12, 1)} for k, v in top]
+        if os.environ.get("BEVBERT_BENCH_VERBOSE"):
+            for r in shape_rows:
+                print("gemm-shape", r, file=sys.stderr)
         roof = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05, all %d launches of one 11-step mix cycle)" % len(rec),
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "peak_source": "%s bf16_tflops_sustained (kernel timed inside a long step)" % peaks["source"],
@@ -272,7 +308,7 @@ def run_ours(args, rank, world, local_rank):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import bevbert_ref as R
-        cores = os.cpu_count() or 1
+        cores = host_cores()
         torch.set_num_threads(cores)
         sd = {k: v.detach().float().cpu().clone().requires_grad_(True) for k, v in model.state_dict().items()}
         ocfg = R.OracleConfig(cfg, drop_p=0.1, feat_drop_p=0.1)

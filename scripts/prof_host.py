@@ -1,0 +1,45 @@
+"""Host-side (Python / launch) overhead profile of one training step on the GPU box (cProfile, top by self time)."""
+import cProfile
+import os
+import pstats
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+from bench import MIX, full_config  # noqa: E402
+from bevbert_b200 import synth  # noqa: E402
+from bevbert_b200.model.pretrain_cmt import GlocalTextPathCMTPreTraining  # noqa: E402
+
+dev = torch.device("cuda", 0)
+model = synth.det_init_(GlocalTextPathCMTPreTraining(full_config()), seed=3).to(dev).train()
+opt = torch.optim.AdamW(model.parameters(), lr=5e-5, fused=True)
+batches = {t: synth.batch_to(synth.make_batch(synth.SynthConfig(batch_size=32), seed=1, task=t), dev) for t in set(MIX)}
+
+
+def step(t):
+    model(batches[t], t).mean().backward()
+    opt.step()
+    opt.zero_grad(set_to_none=True)
+
+
+for i in range(6):
+    step(MIX[i % 11])
+torch.cuda.synchronize()
+for label, n in (("wall", 11),):
+    t0 = time.perf_counter()
+    for i in range(n):
+        step(MIX[i % 11])
+    t1 = time.perf_counter()          # host time to ENQUEUE the steps
+    torch.cuda.synchronize()
+    t2 = time.perf_counter()
+    print("host enqueue %.2f ms/step, until GPU idle %.2f ms/step" % ((t1 - t0) / n * 1e3, (t2 - t0) / n * 1e3))
+pr = cProfile.Profile()
+pr.enable()
+for i in range(11):
+    step(MIX[i % 11])
+torch.cuda.synchronize()
+pr.disable()
+ps = pstats.Stats(pr)
+ps.sort_stats("tottime").print_stats(35)

@@ -87,6 +87,40 @@ class WeightCache:
         self._c[key] = (ver, buf)
         return buf
 
+    def vec(self, *params):
+        """fp32 concatenation of 1-D parameters (packed Q|K|V bias), cached like the weights."""
+        if len(params) == 1:
+            return params[0].detach()
+        key = ("v",) + tuple(p.data_ptr() for p in params)
+        ver = tuple(p._version for p in params)
+        ent = self._c.get(key)
+        if ent is not None and ent[0] == ver:
+            return ent[1]
+        buf = torch.cat([p.detach() for p in params])
+        self._c[key] = (ver, buf)
+        return buf
+
+
+class ZeroPool:
+    """One zero-filled fp32 allocation per backward block, carved into the accumulate-into buffers
+    (split-K weight gradients, bias / LayerNorm reductions): one memset instead of one per tensor."""
+
+    def __init__(self, device, *shapes):
+        sizes = []
+        for sh in shapes:
+            n = 1
+            for d in sh:
+                n *= d
+            sizes.append((n + 3) // 4 * 4)          # keep every slice 16-byte aligned
+        self.buf = torch.zeros(sum(sizes), dtype=torch.float32, device=device)
+        self.out, off = [], 0
+        for sh, n in zip(shapes, sizes):
+            m = 1
+            for d in sh:
+                m *= d
+            self.out.append(self.buf[off:off + m].view(sh))
+            off += n
+
 
 def _empty(shape, like, dtype=None):
     return torch.empty(shape, dtype=dtype or K.act_dtype(), device=like.device)
@@ -117,11 +151,13 @@ def lin_bwd_dx(dy, w16, epi_mul=K.EPI_NONE, aux_in=None, add_in=None, drop=NO_DR
     return out
 
 
-def lin_bwd_dw(dy, x):
-    """dW = dy^T @ x in fp32: dy (M,N), x (M,Kd), both read MN-major, split over the token dimension."""
+def lin_bwd_dw(dy, x, out=None):
+    """dW = dy^T @ x in fp32: dy (M,N), x (M,Kd), both read MN-major, split over the token dimension.
+    `out` (zero-filled fp32 (N,Kd)) is accumulated into when given."""
     M, N = dy.shape
     Kd = x.shape[1]
-    out = torch.zeros(N, Kd, dtype=torch.float32, device=dy.device)
+    if out is None:
+        out = torch.zeros(N, Kd, dtype=torch.float32, device=dy.device)
     tiles = ((N + 127) // 128) * ((Kd + 255) // 256)
     kb = (M + 63) // 64
     split = max(1, min((2 * 148) // max(tiles, 1), kb // 4 if kb >= 4 else 1))
@@ -177,7 +213,7 @@ def attn_sublayer_fwd(st, wc, x, c, kmask, bias, p, H, eps, ds, p_attn, p_hidden
     if c is None:
         nk = nq
         wqkv = wc.get(p[0], p[2], p[4])
-        bqkv = torch.cat([p[1], p[3], p[5]]).detach()
+        bqkv = wc.vec(p[1], p[3], p[5])
         qkv, _ = lin_fwd(x2, wqkv, bqkv)
         q, k, v = qkv, qkv[:, Hd:], qkv[:, 2 * Hd:]
         ldq = ldk = ldv = 3 * Hd
@@ -187,7 +223,7 @@ def attn_sublayer_fwd(st, wc, x, c, kmask, bias, p, H, eps, ds, p_attn, p_hidden
         c2 = c.reshape(B * nk, Hd)
         q, _ = lin_fwd(x2, wc.get(p[0]), p[1].detach())
         wkv = wc.get(p[2], p[4])
-        kv, _ = lin_fwd(c2, wkv, torch.cat([p[3], p[5]]).detach())
+        kv, _ = lin_fwd(c2, wkv, wc.vec(p[3], p[5]))
         k, v = kv, kv[:, Hd:]
         ldq, ldk, ldv = Hd, 2 * Hd, 2 * Hd
         st.update(q=q, kv=kv, c2=c2)
@@ -205,22 +241,28 @@ def attn_sublayer_bwd(st, wc, dy, p, H, want_dbias=False):
     B, Hh, nq, nk, dh, ldp = st["geo"]
     Hd = x2.shape[1]
     dev = x2.device
-    dg = torch.zeros(Hd, dtype=torch.float32, device=dev)
-    db = torch.zeros(Hd, dtype=torch.float32, device=dev)
+    cross = st["cross"]
+    shapes = [(Hd,), (Hd,), (Hd, Hd), (Hd,)]                       # dgamma, dbeta, dWo, dbo
+    shapes += [(Hd, Hd), (Hd,), (2 * Hd, Hd), (2 * Hd,)] if cross else [(3 * Hd, Hd), (3 * Hd,)]
+    if want_dbias:
+        shapes.append((B, nq, nk))
+    z = ZeroPool(dev, *shapes).out
+    dg, db, dWo, dbo = z[0], z[1], z[2], z[3]
+    dbias = z[-1] if want_dbias else None
     dao, dres = K.layernorm_bwd(dy.reshape(-1, Hd), ao, x2, p[8].detach(), st["mean"], st["rstd"], drop_in=st["hdrop"],
                                 want_dres=True, dgamma=dg, dbeta=db)
-    dWo = lin_bwd_dw(dao, ctx)
-    dbo = K.colsum(dao, Hd)
+    lin_bwd_dw(dao, ctx, dWo)
+    K.colsum(dao, Hd, out=dbo)
     dctx = lin_bwd_dx(dao, wc.get(p[6]))
-    dbias = torch.zeros(B, nq, nk, dtype=torch.float32, device=dev) if want_dbias else None
-    if not st["cross"]:
+    if not cross:
         qkv = st["qkv"]
         dqkv = _empty(qkv.shape, qkv)
         L = 3 * Hd
         attn_core_bwd(st, dctx, qkv, L, qkv[:, Hd:], L, qkv[:, 2 * Hd:], L, dqkv, L, dqkv[:, Hd:], L,
                       dqkv[:, 2 * Hd:], L, dbias)
-        dW = lin_bwd_dw(dqkv, x2)
-        dbq = K.colsum(dqkv, L)
+        dW, dbq = z[4], z[5]
+        lin_bwd_dw(dqkv, x2, dW)
+        K.colsum(dqkv, L, out=dbq)
         dx = lin_bwd_dx(dqkv, wc.get(p[0], p[2], p[4]), add_in=dres)
         grads = [dW[:Hd], dbq[:Hd], dW[Hd:2 * Hd], dbq[Hd:2 * Hd], dW[2 * Hd:], dbq[2 * Hd:], dWo, dbo, dg, db]
         return dx, None, grads, dbias
@@ -228,11 +270,12 @@ def attn_sublayer_bwd(st, wc, dy, p, H, want_dbias=False):
     dq = _empty(q.shape, q)
     dkv = _empty(kv.shape, kv)
     attn_core_bwd(st, dctx, q, Hd, kv, 2 * Hd, kv[:, Hd:], 2 * Hd, dq, Hd, dkv, 2 * Hd, dkv[:, Hd:], 2 * Hd, dbias)
-    dWq = lin_bwd_dw(dq, x2)
-    dbq = K.colsum(dq, Hd)
+    dWq, dbq, dWkv, dbkv = z[4], z[5], z[6], z[7]
+    lin_bwd_dw(dq, x2, dWq)
+    K.colsum(dq, Hd, out=dbq)
     dx = lin_bwd_dx(dq, wc.get(p[0]), add_in=dres)
-    dWkv = lin_bwd_dw(dkv, c2)
-    dbkv = K.colsum(dkv, 2 * Hd)
+    lin_bwd_dw(dkv, c2, dWkv)
+    K.colsum(dkv, 2 * Hd, out=dbkv)
     dc = lin_bwd_dx(dkv, wc.get(p[2], p[4]))
     grads = [dWq, dbq, dWkv[:Hd], dbkv[:Hd], dWkv[Hd:], dbkv[Hd:], dWo, dbo, dg, db]
     return dx, dc, grads, dbias
@@ -251,15 +294,15 @@ def ffn_sublayer_fwd(st, wc, a, p, eps, ds, p_hidden):
 def ffn_sublayer_bwd(st, wc, dy, p):
     a, h, hpre, fo = st["f_a"], st["f_h"], st["f_hpre"], st["f_fo"]
     Hd = a.shape[1]
-    dg = torch.zeros(Hd, dtype=torch.float32, device=a.device)
-    db = torch.zeros(Hd, dtype=torch.float32, device=a.device)
+    Fd = hpre.shape[1]
+    dg, db, dW2, db2, dW1, db1 = ZeroPool(a.device, (Hd,), (Hd,), (Hd, Fd), (Hd,), (Fd, Hd), (Fd,)).out
     dfo, dres = K.layernorm_bwd(dy, fo, a, p[4].detach(), st["f_mean"], st["f_rstd"], drop_in=st["f_drop"],
                                 want_dres=True, dgamma=dg, dbeta=db)
-    dW2 = lin_bwd_dw(dfo, h)
-    db2 = K.colsum(dfo, Hd)
+    lin_bwd_dw(dfo, h, dW2)
+    K.colsum(dfo, Hd, out=db2)
     dhpre = lin_bwd_dx(dfo, wc.get(p[2]), epi_mul=K.EPI_DGELU, aux_in=hpre)
-    dW1 = lin_bwd_dw(dhpre, a)
-    db1 = K.colsum(dhpre, hpre.shape[1])
+    lin_bwd_dw(dhpre, a, dW1)
+    K.colsum(dhpre, Fd, out=db1)
     da = lin_bwd_dx(dhpre, wc.get(p[0]), add_in=dres)
     return da, [dW1, db1, dW2, db2, dg, db]
 

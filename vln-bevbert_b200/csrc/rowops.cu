@@ -301,14 +301,8 @@ layernorm_bwd_kernel(const DYT* __restrict__ dy, const XT* __restrict__ x, const
                      const float* __restrict__ rstd_in, long long rows, int H, uint64_t seed_in, uint32_t thresh_in,
                      float scale_in, uint64_t seed_out, uint32_t thresh_out, float scale_out, DXT* __restrict__ dx,
                      bf16* __restrict__ dres, float* __restrict__ dgamma, float* __restrict__ dbeta) {
-  __shared__ float sg[LN_MAXCH * 256];
-  __shared__ float sb[LN_MAXCH * 256];
+  extern __shared__ float ln_part[];  // [2][LN_WARPS][H] per-warp partial dgamma / dbeta (no atomics, no conflicts)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int i = threadIdx.x; i < LN_MAXCH * 256; i += blockDim.x) {
-    sg[i] = 0.f;
-    sb[i] = 0.f;
-  }
-  __syncthreads();
   float pg[LN_MAXCH][8], pb[LN_MAXCH][8];
 #pragma unroll
   for (int c = 0; c < LN_MAXCH; ++c)
@@ -371,21 +365,26 @@ layernorm_bwd_kernel(const DYT* __restrict__ dy, const XT* __restrict__ x, const
     }
   }
   if (dgamma || dbeta) {
+    float* sg = ln_part;
+    float* sb = ln_part + LN_WARPS * H;
 #pragma unroll
     for (int c = 0; c < LN_MAXCH; ++c) {
       const int col = c * 256 + lane * 8;
       if (col < H) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          atomicAdd(&sg[col + j], pg[c][j]);
-          atomicAdd(&sb[col + j], pb[c][j]);
-        }
+        store8(sg + warp * H + col, pg[c]);
+        store8(sb + warp * H + col, pb[c]);
       }
     }
     __syncthreads();
     for (int i = threadIdx.x; i < H; i += blockDim.x) {
-      if (dgamma) atomicAdd(dgamma + i, sg[i]);
-      if (dbeta) atomicAdd(dbeta + i, sb[i]);
+      float a = 0.f, b = 0.f;
+#pragma unroll
+      for (int w = 0; w < LN_WARPS; ++w) {
+        a += sg[w * H + i];
+        b += sb[w * H + i];
+      }
+      if (dgamma) atomicAdd(dgamma + i, a);
+      if (dbeta) atomicAdd(dbeta + i, b);
     }
   }
 }
@@ -750,10 +749,23 @@ extern "C" int bb_layernorm_bwd(const void* dy, int dy_f32, const void* x, int x
   if (rows <= 0) return 0;
   if (H % 8 != 0 || H > LN_MAXCH * 256) return set_error("bb_layernorm_bwd: H must be a multiple of 8 and <= 1024");
   long long g = (rows + LN_WARPS - 1) / LN_WARPS;
-  if (g > 148 * 4) g = 148 * 4;
+  if (g > 148 * 2) g = 148 * 2;
   const unsigned grid = (unsigned)g;
+  const size_t ln_smem = (size_t)2 * LN_WARPS * H * sizeof(float);
+  {
+    static bool attr_done = false;
+    if (!attr_done) {
+      cudaFuncSetAttribute(layernorm_bwd_kernel<bf16, bf16, bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
+      cudaFuncSetAttribute(layernorm_bwd_kernel<bf16, float, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
+      cudaFuncSetAttribute(layernorm_bwd_kernel<float, bf16, bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
+      cudaFuncSetAttribute(layernorm_bwd_kernel<float, float, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
+      cudaFuncSetAttribute(layernorm_bwd_kernel<bf16, bf16, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
+      cudaFuncSetAttribute(layernorm_bwd_kernel<bf16, float, bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
+      attr_done = true;
+    }
+  }
 #define LN_BWD(DYT, XT, DXT)                                                                                        \
-  layernorm_bwd_kernel<DYT, XT, DXT><<<grid, LN_WARPS * 32, 0, STREAM>>>(                                           \
+  layernorm_bwd_kernel<DYT, XT, DXT><<<grid, LN_WARPS * 32, ln_smem, STREAM>>>(                                     \
       (const DYT*)dy, (const XT*)x, (const bf16*)residual, gamma, mean, rstd, rows, H, seed_in, thresh_in, scale_in, \
       seed_out, thresh_out, scale_out, (DXT*)dx, (bf16*)dres, dgamma, dbeta)
   if (!dy_f32 && !x_f32 && !dx_f32) LN_BWD(bf16, bf16, bf16);

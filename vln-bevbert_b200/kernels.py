@@ -25,7 +25,13 @@ def _p(t):
     return 0 if t is None else t.data_ptr()
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def _stream():
+    """raw cudaStream_t of torch's current stream on the current device (fast path avoids building a Stream object)."""
+    if _raw_stream is not None:
+        return _raw_stream(torch.cuda.current_device())
     return torch.cuda.current_stream().cuda_stream
 
 
