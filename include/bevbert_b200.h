@@ -171,6 +171,55 @@ int bb_axpy_f32_from_bf16(const void* x, float* y, int64_t n, void* stream);    
 int bb_softmax_xent(const float* logits, const int64_t* labels, int64_t rows, int V, int64_t ld, float* loss,
                     const float* gscale, void* dlogits, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Native sub-layer executors: ONE call enqueues the whole kernel sequence of a sub-layer on `stream`.
+ *   attention sub-layer = LN(dropout(dense(attention(x, c))) + x)     (vilmodel.py:103-166, 325-363)
+ *   FFN sub-layer       = LN(dropout(W2 gelu(W1 a + b1) + b2) + a)     (vilmodel.py:168-193)
+ * The caller provides a forward workspace `ws` (kept until backward) and a backward scratch `gws`, sized by
+ * bb_*_ws_bytes; parameter-gradient buffers are fp32, zero-filled by the caller and accumulated into.
+ * Weights are bf16 (out,in) row-major; self-attention uses the row-stacked Q|K|V weight (3Hd,Hd) in w_qkv,
+ * cross-attention Wq in w_qkv and the stacked K|V weight (2Hd,Hd) in w_kv.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct bb_attn_desc {
+  int32_t B, nq, nk, Hd, heads;
+  int32_t cross;      /* 0: self-attention (c unused, nk == nq), 1: cross-attention over context c */
+  int32_t want_dbias; /* backward: accumulate d(bias) (graph bias of the global map encoder) */
+  float eps;
+  const void* x;      /* (B*nq, Hd) bf16 queries / residual */
+  const void* c;      /* (B*nk, Hd) bf16 context or NULL */
+  const float* kmask; /* (B, nk) additive key mask or NULL */
+  const float* bias;  /* (B, nq, nk) additive bias shared by heads or NULL */
+  const void* w_qkv; const void* w_kv; const void* w_o;
+  const float* b_qkv; const float* b_kv; const float* b_o; const float* gamma; const float* beta;
+  uint64_t seed_attn; uint32_t th_attn; float sc_attn; /* attention-probability dropout */
+  uint64_t seed_h; uint32_t th_h; float sc_h;          /* hidden dropout before the residual add */
+  void* ws;  /* forward workspace */
+  void* y;   /* (B*nq, Hd) bf16 output */
+  /* backward only */
+  const void* dy; void* gws; void* dx; void* dc;
+  float* dw_qkv; float* db_qkv; float* dw_kv; float* db_kv; float* dw_o; float* db_o; float* dgamma; float* dbeta;
+  float* dbias;
+} bb_attn_desc;
+int bb_attn_ws_bytes(const bb_attn_desc* d, int64_t* fwd_bytes, int64_t* bwd_bytes);
+int bb_attn_fwd(const bb_attn_desc* d, void* stream);
+int bb_attn_bwd(const bb_attn_desc* d, void* stream);
+
+typedef struct bb_ffn_desc {
+  int64_t M;          /* rows (tokens) */
+  int32_t Hd, Fd;     /* hidden and intermediate sizes */
+  float eps;
+  const void* a;      /* (M, Hd) bf16 input / residual */
+  const void* w1; const void* w2; const float* b1; const float* b2; const float* gamma; const float* beta;
+  uint64_t seed_h; uint32_t th_h; float sc_h;
+  void* ws; void* y;
+  /* backward only */
+  const void* dy; void* gws; void* da;
+  float* dw1; float* db1; float* dw2; float* db2; float* dgamma; float* dbeta;
+} bb_ffn_desc;
+int bb_ffn_ws_bytes(const bb_ffn_desc* d, int64_t* fwd_bytes, int64_t* bwd_bytes);
+int bb_ffn_fwd(const bb_ffn_desc* d, void* stream);
+int bb_ffn_bwd(const bb_ffn_desc* d, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

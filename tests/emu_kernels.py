@@ -52,6 +52,18 @@ def act_dtype():
     return F32
 
 
+def native_sublayers():
+    """The emulation has no C++ executors: blocks.py falls back to its Python composition of the same kernels."""
+    return False
+
+
+def _no_native(*a, **k):
+    raise RuntimeError("native sub-layer executors are not emulated")
+
+
+attn_desc = ffn_desc = sublayer_ws_bytes = sublayer_fwd = sublayer_bwd = _no_native
+
+
 def drop_params(p):
     return (0, 1.0) if p <= 0 else (min(int(p * 4294967296.0), 4294967295), 1.0 / (1.0 - p))
 
@@ -257,7 +269,7 @@ def softmax_xent(logits, labels, V, ld, want_grad=True):
     return loss, dl
 
 
-_NAMES = ["gemm", "act_dtype", "drop_params", "launch_count", "reset_launch_count", "bev_lift_index",
+_NAMES = ["native_sublayers", "attn_desc", "ffn_desc", "sublayer_ws_bytes", "sublayer_fwd", "sublayer_bwd", "gemm", "act_dtype", "drop_params", "launch_count", "reset_launch_count", "bev_lift_index",
           "bev_scatter_mean", "bev_scatter_sem", "cast_to_act", "cast_to_f32", "dropout_act", "layernorm_fwd",
           "layernorm_bwd", "colsum", "softmax_fwd", "softmax_bwd", "embed_sum", "embed_scatter_grad", "gather_rows",
           "scatter_add_rows", "gelu_bwd", "relu_bwd", "add_rows", "scale_rows_", "segment_wsum", "segment_wsum_bwd",

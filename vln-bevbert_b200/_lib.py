@@ -36,6 +36,23 @@ class GemmArgs(C.Structure):
     ]
 
 
+class AttnDesc(C.Structure):
+    """struct bb_attn_desc (include/bevbert_b200.h)."""
+    _fields_ = [(n, c_i32) for n in ("B", "nq", "nk", "Hd", "heads", "cross", "want_dbias")] + [("eps", c_float)] + \
+        [(n, c_void_p) for n in ("x", "c", "kmask", "bias", "w_qkv", "w_kv", "w_o", "b_qkv", "b_kv", "b_o", "gamma", "beta")] + \
+        [("seed_attn", c_u64), ("th_attn", c_u32), ("sc_attn", c_float), ("seed_h", c_u64), ("th_h", c_u32), ("sc_h", c_float)] + \
+        [(n, c_void_p) for n in ("ws", "y", "dy", "gws", "dx", "dc", "dw_qkv", "db_qkv", "dw_kv", "db_kv", "dw_o", "db_o",
+                                  "dgamma", "dbeta", "dbias")]
+
+
+class FfnDesc(C.Structure):
+    """struct bb_ffn_desc (include/bevbert_b200.h)."""
+    _fields_ = [("M", c_i64), ("Hd", c_i32), ("Fd", c_i32), ("eps", c_float)] + \
+        [(n, c_void_p) for n in ("a", "w1", "w2", "b1", "b2", "gamma", "beta")] + \
+        [("seed_h", c_u64), ("th_h", c_u32), ("sc_h", c_float)] + \
+        [(n, c_void_p) for n in ("ws", "y", "dy", "gws", "da", "dw1", "db1", "dw2", "db2", "dgamma", "dbeta")]
+
+
 # name -> (restype, argtypes); mirrors include/bevbert_b200.h one to one
 _SIGNATURES = {
     "bb_last_error": (C.c_char_p, []),
@@ -73,6 +90,12 @@ _SIGNATURES = {
     "bb_segment_wsum_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_int, c_void_p, c_void_p]),
     "bb_add_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_void_p]),
     "bb_axpy_f32_from_bf16": (c_int, [c_void_p, c_void_p, c_i64, c_void_p]),
+    "bb_attn_ws_bytes": (c_int, [C.POINTER(AttnDesc), C.POINTER(c_i64), C.POINTER(c_i64)]),
+    "bb_attn_fwd": (c_int, [C.POINTER(AttnDesc), c_void_p]),
+    "bb_attn_bwd": (c_int, [C.POINTER(AttnDesc), c_void_p]),
+    "bb_ffn_ws_bytes": (c_int, [C.POINTER(FfnDesc), C.POINTER(c_i64), C.POINTER(c_i64)]),
+    "bb_ffn_fwd": (c_int, [C.POINTER(FfnDesc), c_void_p]),
+    "bb_ffn_bwd": (c_int, [C.POINTER(FfnDesc), c_void_p]),
     "bb_softmax_xent": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_i64, c_void_p, c_void_p, c_void_p, c_void_p]),
 }
 

@@ -158,10 +158,16 @@ def lin_bwd_dw(dy, x, out=None):
     Kd = x.shape[1]
     if out is None:
         out = torch.zeros(N, Kd, dtype=torch.float32, device=dy.device)
-    tiles = ((N + 127) // 128) * ((Kd + 255) // 256)
+    # few output tiles (weights are small) but a long reduction over tokens: prefer 128-wide tiles when 256-wide
+    # ones cannot fill half the SMs, then split the token dimension until ~148 CTAs, keeping >= 8 k-blocks per split
+    m_t = (N + 127) // 128
+    bn = 256 if m_t * ((Kd + 255) // 256) >= 74 else 128
+    if Kd <= bn:
+        bn = 0
+    tiles = m_t * ((Kd + max(bn, 1) - 1) // max(bn, 1)) if bn else m_t
     kb = (M + 63) // 64
-    split = max(1, min((2 * 148) // max(tiles, 1), kb // 4 if kb >= 4 else 1))
-    K.gemm(dy, x, out, N, Kd, M, lda=N, ldb=Kd, ldd=Kd, a_mn=True, b_mn=True, split_k=split)
+    split = max(1, min((148 + tiles // 2) // max(tiles, 1), kb // 8 if kb >= 8 else 1))
+    K.gemm(dy, x, out, N, Kd, M, lda=N, ldb=Kd, ldd=Kd, a_mn=True, b_mn=True, split_k=split, block_n=bn)
     return out
 
 
@@ -307,6 +313,125 @@ def ffn_sublayer_bwd(st, wc, dy, p):
     return da, [dW1, db1, dW2, db2, dg, db]
 
 
+# =============================================================================================== native sub-layers
+def _ws(nbytes, dev):
+    return torch.empty(nbytes, dtype=torch.uint8, device=dev)
+
+
+def attn_native_fwd(st, rt, x, c, kmask, bias, p, H, eps, p_attn, p_hidden):
+    """Same math as attn_sublayer_fwd, enqueued by one C call (csrc/layers.cu bb_attn_fwd)."""
+    wc, ds = rt.wc, rt.ds
+    B, nq, Hd = x.shape
+    dev = x.device
+    x2 = x.reshape(B * nq, Hd)
+    if not x2.is_contiguous():
+        x2 = x2.contiguous()
+    d = K.attn_desc()
+    d.B, d.nq, d.Hd, d.heads, d.eps = B, nq, Hd, H, eps
+    keep = [x2, kmask, bias]
+    d.x = x2.data_ptr()
+    if c is None:
+        d.nk, d.cross = nq, 0
+        wq, bq = wc.get(p[0], p[2], p[4]), wc.vec(p[1], p[3], p[5])
+        d.w_qkv, d.b_qkv = wq.data_ptr(), bq.data_ptr()
+        keep += [wq, bq]
+    else:
+        nk = c.shape[1]
+        c2 = c.reshape(B * nk, Hd)
+        if not c2.is_contiguous():
+            c2 = c2.contiguous()
+        d.nk, d.cross, d.c = nk, 1, c2.data_ptr()
+        wq, bq, wkv, bkv = wc.get(p[0]), p[1].detach(), wc.get(p[2], p[4]), wc.vec(p[3], p[5])
+        d.w_qkv, d.b_qkv, d.w_kv, d.b_kv = wq.data_ptr(), bq.data_ptr(), wkv.data_ptr(), bkv.data_ptr()
+        keep += [c2, wq, bq, wkv, bkv]
+    wo = wc.get(p[6])
+    d.w_o, d.b_o, d.gamma, d.beta = wo.data_ptr(), p[7].data_ptr(), p[8].data_ptr(), p[9].data_ptr()
+    keep.append(wo)
+    d.kmask = kmask.data_ptr() if kmask is not None else None
+    d.bias = bias.data_ptr() if bias is not None else None
+    d.seed_attn, d.th_attn, d.sc_attn = ds.make(p_attn)
+    d.seed_h, d.th_h, d.sc_h = ds.make(p_hidden)
+    fb, bb_ = K.sublayer_ws_bytes(d)
+    ws = _ws(fb, dev)
+    y = torch.empty(B * nq, Hd, dtype=K.act_dtype(), device=dev)
+    d.ws, d.y = ws.data_ptr(), y.data_ptr()
+    K.sublayer_fwd(d)
+    st.update(a_d=d, a_keep=keep, a_ws=ws, a_bwd=bb_, a_geo=(B, nq, d.nk, Hd), a_cross=c is not None)
+    return y.view(B, nq, Hd)
+
+
+def attn_native_bwd(st, dy, want_dbias=False):
+    d = st["a_d"]
+    B, nq, nk, Hd = st["a_geo"]
+    cross = st["a_cross"]
+    dev = dy.device
+    dy = dy.reshape(-1, Hd)
+    if not dy.is_contiguous():
+        dy = dy.contiguous()
+    shapes = [(Hd,), (Hd,), (Hd, Hd), (Hd,)]
+    shapes += [(Hd, Hd), (Hd,), (2 * Hd, Hd), (2 * Hd,)] if cross else [(3 * Hd, Hd), (3 * Hd,)]
+    if want_dbias:
+        shapes.append((B, nq, nk))
+    z = ZeroPool(dev, *shapes).out
+    gws = _ws(st["a_bwd"], dev)
+    dx = torch.empty(B * nq, Hd, dtype=K.act_dtype(), device=dev)
+    dc = torch.empty(B * nk, Hd, dtype=K.act_dtype(), device=dev) if cross else None
+    d.dy, d.gws, d.dx = dy.data_ptr(), gws.data_ptr(), dx.data_ptr()
+    d.dc = dc.data_ptr() if cross else None
+    d.dgamma, d.dbeta, d.dw_o, d.db_o = z[0].data_ptr(), z[1].data_ptr(), z[2].data_ptr(), z[3].data_ptr()
+    d.dw_qkv, d.db_qkv = z[4].data_ptr(), z[5].data_ptr()
+    if cross:
+        d.dw_kv, d.db_kv = z[6].data_ptr(), z[7].data_ptr()
+    d.want_dbias = int(want_dbias)
+    d.dbias = z[-1].data_ptr() if want_dbias else None
+    K.sublayer_bwd(d)
+    dbias = z[-1] if want_dbias else None
+    if not cross:
+        dW, dbq = z[4], z[5]
+        grads = [dW[:Hd], dbq[:Hd], dW[Hd:2 * Hd], dbq[Hd:2 * Hd], dW[2 * Hd:], dbq[2 * Hd:], z[2], z[3], z[0], z[1]]
+    else:
+        dWkv, dbkv = z[6], z[7]
+        grads = [z[4], z[5], dWkv[:Hd], dbkv[:Hd], dWkv[Hd:], dbkv[Hd:], z[2], z[3], z[0], z[1]]
+    return dx, dc, grads, dbias
+
+
+def ffn_native_fwd(st, rt, a, p, eps, p_hidden):
+    wc = rt.wc
+    M, Hd = a.shape
+    dev = a.device
+    if not a.is_contiguous():
+        a = a.contiguous()
+    w1, w2 = wc.get(p[0]), wc.get(p[2])
+    d = K.ffn_desc()
+    d.M, d.Hd, d.Fd, d.eps = M, Hd, w1.shape[0], eps
+    d.a, d.w1, d.w2 = a.data_ptr(), w1.data_ptr(), w2.data_ptr()
+    d.b1, d.b2, d.gamma, d.beta = p[1].data_ptr(), p[3].data_ptr(), p[4].data_ptr(), p[5].data_ptr()
+    d.seed_h, d.th_h, d.sc_h = rt.ds.make(p_hidden)
+    fb, bb_ = K.sublayer_ws_bytes(d)
+    ws = _ws(fb, dev)
+    y = torch.empty(M, Hd, dtype=K.act_dtype(), device=dev)
+    d.ws, d.y = ws.data_ptr(), y.data_ptr()
+    K.sublayer_fwd(d)
+    st.update(f_d=d, f_keep=[a, w1, w2], f_ws=ws, f_bwd=bb_, f_dims=(M, Hd, w1.shape[0]))
+    return y
+
+
+def ffn_native_bwd(st, dy):
+    d = st["f_d"]
+    M, Hd, Fd = st["f_dims"]
+    dev = dy.device
+    if not dy.is_contiguous():
+        dy = dy.contiguous()
+    dg, db, dW2, db2, dW1, db1 = ZeroPool(dev, (Hd,), (Hd,), (Hd, Fd), (Hd,), (Fd, Hd), (Fd,)).out
+    gws = _ws(st["f_bwd"], dev)
+    da = torch.empty(M, Hd, dtype=K.act_dtype(), device=dev)
+    d.dy, d.gws, d.da = dy.data_ptr(), gws.data_ptr(), da.data_ptr()
+    d.dgamma, d.dbeta, d.dw2, d.db2, d.dw1, d.db1 = (dg.data_ptr(), db.data_ptr(), dW2.data_ptr(), db2.data_ptr(),
+                                                     dW1.data_ptr(), db1.data_ptr())
+    K.sublayer_bwd(d)
+    return da, [dW1, db1, dW2, db2, dg, db]
+
+
 # =============================================================================================== block impls
 class BertLayerImpl:
     """BertLayer (vilmodel.py:195-208): self-attention sub-layer + FFN sub-layer, post-LN.
@@ -318,16 +443,25 @@ class BertLayerImpl:
     def fwd(self, st, inputs, p):
         x, kmask, bias = inputs
         ds = self.rt.ds
-        a = attn_sublayer_fwd(st, self.wc, x, None, kmask, bias, p[:10], self.H, self.eps, ds, self.pa, self.ph)
-        y = ffn_sublayer_fwd(st, self.wc, a.reshape(-1, a.shape[-1]), p[10:], self.eps, ds, self.ph)
         st["shape"] = x.shape
         st["bias_grad"] = bias is not None and bias.requires_grad
+        st["native"] = K.native_sublayers()
+        if st["native"]:
+            a = attn_native_fwd(st, self.rt, x, None, kmask, bias, p[:10], self.H, self.eps, self.pa, self.ph)
+            y = ffn_native_fwd(st, self.rt, a.reshape(-1, a.shape[-1]), p[10:], self.eps, self.ph)
+        else:
+            a = attn_sublayer_fwd(st, self.wc, x, None, kmask, bias, p[:10], self.H, self.eps, ds, self.pa, self.ph)
+            y = ffn_sublayer_fwd(st, self.wc, a.reshape(-1, a.shape[-1]), p[10:], self.eps, ds, self.ph)
         return y.view(x.shape)
 
     def bwd(self, st, gouts, p):
         dy = gouts[0].reshape(-1, st["shape"][-1])
-        da, g_ffn = ffn_sublayer_bwd(st, self.wc, dy, p[10:])
-        dx, _, g_att, dbias = attn_sublayer_bwd(st, self.wc, da, p[:10], self.H, want_dbias=st["bias_grad"])
+        if st["native"]:
+            da, g_ffn = ffn_native_bwd(st, dy)
+            dx, _, g_att, dbias = attn_native_bwd(st, da, want_dbias=st["bias_grad"])
+        else:
+            da, g_ffn = ffn_sublayer_bwd(st, self.wc, dy, p[10:])
+            dx, _, g_att, dbias = attn_sublayer_bwd(st, self.wc, da, p[:10], self.H, want_dbias=st["bias_grad"])
         return [dx.view(st["shape"]), None, dbias], g_att + g_ffn
 
 
@@ -341,10 +475,17 @@ class XAttnImpl:
     def fwd(self, st, inputs, p):
         x, c, cmask = inputs
         st["xs"], st["cs"] = x.shape, c.shape
+        st["native"] = K.native_sublayers()
+        if st["native"]:
+            return attn_native_fwd(st, self.rt, x, c, cmask, None, p, self.H, self.eps, self.pa, self.ph)
         return attn_sublayer_fwd(st, self.wc, x, c, cmask, None, p, self.H, self.eps, self.rt.ds, self.pa, self.ph)
 
     def bwd(self, st, gouts, p):
-        dx, dc, grads, _ = attn_sublayer_bwd(st, self.wc, gouts[0].reshape(-1, st["xs"][-1]), p, self.H)
+        dy = gouts[0].reshape(-1, st["xs"][-1])
+        if st["native"]:
+            dx, dc, grads, _ = attn_native_bwd(st, dy)
+        else:
+            dx, dc, grads, _ = attn_sublayer_bwd(st, self.wc, dy, p, self.H)
         return [dx.view(st["xs"]), dc.view(st["cs"]), None], grads
 
 

@@ -85,6 +85,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   uint64_t* tmem_full = empty_bar + MAX_STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* sbias = reinterpret_cast<float*>(smem + p.stages * stage_bytes + 512);  // [2][256], one per accumulator
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -200,6 +201,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const bool row_ok = row < p.M;
       const long long row_off = (long long)t.b1 * p.d_s1 + (long long)t.b2 * p.d_s2 + (long long)row * p.ldd;
       const bool add_bias = p.bias != nullptr && t.split == 0;
+      if (p.bias != nullptr) {
+        // stage this tile's bias slice in shared memory (one coalesced read instead of 16 dependent loads per chunk)
+        float* sb = sbias + acc * 256;
+        const int e = (warp - 2) * 32 + lane;  // 0..127
+        for (int i = e; i < p.block_n; i += 128) sb[i] = (n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.0f;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
 
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
@@ -216,9 +224,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) * p.alpha;
         const bool full = (col0 + 16 <= p.N);
         if (add_bias) {
+          const float4* sb4 = reinterpret_cast<const float4*>(sbias + acc * 256 + c);
 #pragma unroll
-          for (int i = 0; i < 16; ++i)
-            if (full || col0 + i < p.N) v[i] += __ldg(p.bias + col0 + i);
+          for (int i = 0; i < 4; ++i) {
+            const float4 bv = sb4[i];
+            v[4 * i] += bv.x;
+            v[4 * i + 1] += bv.y;
+            v[4 * i + 2] += bv.z;
+            v[4 * i + 3] += bv.w;
+          }
         }
         const long long off = row_off + col0;
         if (p.aux_out != nullptr) {
@@ -282,8 +296,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         if (p.out_f32) {
           float* D = reinterpret_cast<float*>(p.D) + off;
           if (p.atomic) {
-            for (int i = 0; i < 16; ++i)
-              if (full || col0 + i < p.N) atomicAdd(D + i, v[i]);
+            if (full && p.vec_ok) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(D + 4 * i), "f"(v[4 * i]),
+                             "f"(v[4 * i + 1]), "f"(v[4 * i + 2]), "f"(v[4 * i + 3])
+                             : "memory");
+            } else {
+              for (int i = 0; i < 16; ++i)
+                if (col0 + i < p.N) atomicAdd(D + i, v[i]);
+            }
           } else if (full && p.vec_ok) {
             float4* dst = reinterpret_cast<float4*>(D);
 #pragma unroll
@@ -461,11 +483,11 @@ extern "C" int bb_gemm_bf16(const bb_gemm_args* a, void* stream_) {
   }
 
   const int stage_bytes = A_STAGE_BYTES + bn * BLOCK_K * 2;
-  int stages = (g_smem_optin - 1024 - 512) / stage_bytes;
+  int stages = (g_smem_optin - 1024 - 512 - 2048) / stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (stages < 2) return set_error("bb_gemm_bf16: not enough shared memory for 2 stages");
   p.stages = stages;
-  const size_t smem_bytes = (size_t)stages * stage_bytes + 1024 + 512;
+  const size_t smem_bytes = (size_t)stages * stage_bytes + 1024 + 512 + 2048;
 
   CUtensorMap ta, tb;
   int e;

@@ -92,6 +92,40 @@ def gemm(a, b, out, M, N, K, lda, ldb, ldd, a_mn=False, b_mn=False, nb1=1, nb2=1
     return out
 
 
+# ---------------------------------------------------------------------------------------------- native sub-layers
+def native_sublayers():
+    """True: blocks.py hands whole attention / FFN sub-layers to the C++ executors (csrc/layers.cu)."""
+    return True
+
+
+def attn_desc():
+    return _lib.AttnDesc()
+
+
+def ffn_desc():
+    return _lib.FfnDesc()
+
+
+def sublayer_ws_bytes(d):
+    lib = _lib.load()
+    f, b = C.c_int64(), C.c_int64()
+    fn = lib.bb_attn_ws_bytes if isinstance(d, _lib.AttnDesc) else lib.bb_ffn_ws_bytes
+    _lib.check(fn(C.byref(d), C.byref(f), C.byref(b)), "bb_*_ws_bytes")
+    return f.value, b.value
+
+
+def sublayer_fwd(d):
+    lib = _lib.load()
+    fn = lib.bb_attn_fwd if isinstance(d, _lib.AttnDesc) else lib.bb_ffn_fwd
+    _lib.check(fn(C.byref(d), _stream()), "bb_sublayer_fwd")
+
+
+def sublayer_bwd(d):
+    lib = _lib.load()
+    fn = lib.bb_attn_bwd if isinstance(d, _lib.AttnDesc) else lib.bb_ffn_bwd
+    _lib.check(fn(C.byref(d), _stream()), "bb_sublayer_bwd")
+
+
 # ---------------------------------------------------------------------------------------------- BEV
 def bev_lift_index(depths, T_c2w, S_w2c, T_w2c, map_dim, map_res, depth_scale=10.0, fx=7.0, fy=7.0, cx=7.0, cy=7.0,
                    y_clip=0.5, want_pc=False):
