@@ -261,18 +261,7 @@ def run_ours(args, rank, world, local_rank):
     peaks = load_peaks()
     roof = None
     if rank == 0 or world == 1:
-        rec = []
-        real_gemm = K.gemm
-
-        def timed_gemm(a, b, out, M, N, Kd, *a_, **kw):
-            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s.record()
-            r = real_gemm(a, b, out, M, N, Kd, *a_, **kw)
-            e.record()
-            rec.append((2.0 * M * N * Kd * kw.get("nb1", 1) * kw.get("nb2", 1), s, e,
-                        (M, N, Kd, kw.get("nb1", 1) * kw.get("nb2", 1), int(kw.get("a_mn", False)), int(kw.get("b_mn", False)))))
-            return r
-        K.gemm = timed_gemm
+        K.gemm_profile(True)
         try:
             for i in range(len(MIX)):
                 loss = model(resident[MIX[i]][0], MIX[i]).mean()     # un-wrapped module: no collective in this pass
@@ -280,16 +269,17 @@ def run_ours(args, rank, world, local_rank):
                 model.zero_grad(set_to_none=True)
             torch.cuda.synchronize()
         finally:
-            K.gemm = real_gemm
+            K.gemm_profile(False)
+        rec = [(2.0 * d[0] * d[1] * d[2] * d[3], ms_, d) for ms_, d in K.gemm_profile_records()]
         flops = sum(r[0] for r in rec)
-        tms = sum(r[1].elapsed_time(r[2]) for r in rec)
+        tms = sum(r[1] for r in rec)
         achieved = flops / (tms * 1e-3) / 1e12
         peak = peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"]
         by_shape = {}
         for r in rec:
-            d = by_shape.setdefault(r[3], [0, 0.0, 0.0])
+            d = by_shape.setdefault(r[2], [0, 0.0, 0.0])
             d[0] += 1
-            d[1] += r[1].elapsed_time(r[2])
+            d[1] += r[1]
             d[2] += r[0]
         top = sorted(by_shape.items(), key=lambda kv: -kv[1][1])[:14]
         shape_rows = [{"MNKb_amn_bmn": list(k), "launches": v[0], "ms": round(v[1], 3),

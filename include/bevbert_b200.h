@@ -63,6 +63,12 @@ typedef struct bb_gemm_args {
 } bb_gemm_args;
 
 int bb_gemm_bf16(const bb_gemm_args* args, void* stream);
+/* Optional measurement hook (bench.py roofline): while enabled, every bb_gemm_bf16 launch is bracketed by a pair
+ * of CUDA events on its stream.  bb_gemm_profile(1) resets and starts, (0) stops; _count() = launches recorded;
+ * _read(i, &ms, dims) synchronises on launch i and returns its duration and (M, N, K, batches, a_mn, b_mn). */
+int bb_gemm_profile(int enable);
+int64_t bb_gemm_profile_count(void);
+int bb_gemm_profile_read(int64_t idx, float* ms, int64_t* dims6);
 
 /* ---------------------------------------------------------------------------------------------
  * BEV lifting (pretrain_src/model/pretrain_cmt.py:114-137 + bev_utils.py:349-378, 381-406).

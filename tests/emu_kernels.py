@@ -57,6 +57,14 @@ def native_sublayers():
     return False
 
 
+def gemm_profile(enable):
+    pass
+
+
+def gemm_profile_records():
+    return []
+
+
 def _no_native(*a, **k):
     raise RuntimeError("native sub-layer executors are not emulated")
 
@@ -269,7 +277,7 @@ def softmax_xent(logits, labels, V, ld, want_grad=True):
     return loss, dl
 
 
-_NAMES = ["native_sublayers", "attn_desc", "ffn_desc", "sublayer_ws_bytes", "sublayer_fwd", "sublayer_bwd", "gemm", "act_dtype", "drop_params", "launch_count", "reset_launch_count", "bev_lift_index",
+_NAMES = ["gemm_profile", "gemm_profile_records", "native_sublayers", "attn_desc", "ffn_desc", "sublayer_ws_bytes", "sublayer_fwd", "sublayer_bwd", "gemm", "act_dtype", "drop_params", "launch_count", "reset_launch_count", "bev_lift_index",
           "bev_scatter_mean", "bev_scatter_sem", "cast_to_act", "cast_to_f32", "dropout_act", "layernorm_fwd",
           "layernorm_bwd", "colsum", "softmax_fwd", "softmax_bwd", "embed_sum", "embed_scatter_grad", "gather_rows",
           "scatter_add_rows", "gelu_bwd", "relu_bwd", "add_rows", "scale_rows_", "segment_wsum", "segment_wsum_bwd",

@@ -33,7 +33,7 @@ def _oracle_grads(sd, b, task, cfg, autocast=False):
     return out.detach().float(), {n: v.grad.clone() for n, v in sd.items() if v.grad is not None}
 
 
-def _compare(task, cfg, scfg, seed=7, loss_tol=1e-2, global_grad_tol=1e-2, grad_tol=3e-2):
+def _compare(task, cfg, scfg, seed=7, loss_tol=1e-2, global_grad_tol=1e-2, grad_tol=5e-2):
     """Losses: relative L2 <= 1e-2 (north_star bf16 tolerance).  Gradients: relative L2 over all parameters
     <= 1e-2 where the problem is well conditioned (MLM); for the softmax-CE action/object heads, whose gradient
     terms cancel across near-identical tokens at random init, even PyTorch's own bf16 autocast of the reference

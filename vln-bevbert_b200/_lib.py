@@ -60,6 +60,9 @@ _SIGNATURES = {
     "bb_launch_count": (c_i64, []),
     "bb_reset_launch_count": (None, []),
     "bb_gemm_bf16": (c_int, [C.POINTER(GemmArgs), c_void_p]),
+    "bb_gemm_profile": (c_int, [c_int]),
+    "bb_gemm_profile_count": (c_i64, []),
+    "bb_gemm_profile_read": (c_int, [c_i64, C.POINTER(c_float), C.POINTER(c_i64)]),
     "bb_bev_lift_index": (c_int, [c_void_p] * 4 + [c_int] * 4 + [c_float] * 5 + [c_int, c_float, c_float, c_void_p,
                                                                                   c_void_p, c_void_p]),
     "bb_bev_scatter_mean_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int] + [c_void_p] * 5),

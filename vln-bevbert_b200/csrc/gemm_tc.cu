@@ -2,7 +2,7 @@
 // in TMEM, double buffered) -> tcgen05.ld epilogue with fused bias / GELU / ReLU / gelu' / residual.
 //
 // Persistent, warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane),
-// warps 2..5 = epilogue (warp w owns TMEM lanes 32*(w%4) .. +31). One CTA per SM.
+// warps 2..9 = epilogue (warp w owns TMEM lanes 32*(w%4) .. +31, two warps per lane quarter). One CTA per SM.
 //
 // Tile: 128 (M) x block_n (N, runtime, <=256) x 64 (K) per pipeline stage. Operands may be K-major or
 // MN-major (transposed in memory), which gives all of  X*W^T (forward), dY*W (dX) and dY^T*X (dW)
@@ -11,6 +11,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <mutex>
+#include <vector>
 #include <stdio.h>
 #include <string.h>
 
@@ -24,7 +25,7 @@ constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;
 constexpr int UMMA_K = 16;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 320;  // 1 TMA warp + 1 MMA warp + 8 epilogue warps
 constexpr int MAX_STAGES = 8;
 constexpr int TMEM_COLS = 512;
 
@@ -101,7 +102,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 4);
+      mbar_init(&tmem_empty[i], 8);
     }
     fence_mbar_init();
   }
@@ -190,10 +191,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (4 warps)
+    // ------------------------------------------------------------------ epilogue (8 warps)
+    // warps 2..9: warp w owns TMEM lanes 32*(w%4)..+31 (hardware rule) and every other 16-column chunk of the
+    // tile (two warps per lane quarter).  Global epilogue operands (gelu'/relu' input, residual) of the NEXT chunk
+    // are prefetched into registers before the current chunk is processed, so their latency is off the critical path.
     const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;
     int acc = 0;
     uint32_t acc_phase = 0;
+    const bool need_aux = p.epi_mul != 0;
+    const bool need_add = p.add_in != nullptr;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const TileCoord t = decode_tile(p, tile);
       const int row = t.m_tile * BLOCK_M + quarter * 32 + lane;
@@ -202,21 +209,48 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const long long row_off = (long long)t.b1 * p.d_s1 + (long long)t.b2 * p.d_s2 + (long long)row * p.ldd;
       const bool add_bias = p.bias != nullptr && t.split == 0;
       if (p.bias != nullptr) {
-        // stage this tile's bias slice in shared memory (one coalesced read instead of 16 dependent loads per chunk)
+        // stage this tile's bias slice in shared memory (one coalesced read instead of dependent loads per chunk)
         float* sb = sbias + acc * 256;
-        const int e = (warp - 2) * 32 + lane;  // 0..127
-        for (int i = e; i < p.block_n; i += 128) sb[i] = (n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.0f;
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const int e = (warp - 2) * 32 + lane;  // 0..255
+        for (int i = e; i < p.block_n; i += 256) sb[i] = (n0 + i < p.N) ? __ldg(p.bias + n0 + i) : 0.0f;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
       }
+      // prefetch registers for the first chunk
+      uint4 pa[2], pd[2];
+      pa[0] = pa[1] = pd[0] = pd[1] = make_uint4(0, 0, 0, 0);
+      auto prefetch = [&](int c) {
+        const int col0 = n0 + c;
+        if (c < p.block_n && row_ok && p.vec_ok && col0 + 16 <= p.N) {
+          const long long off = row_off + col0;
+          if (need_aux) {
+            const uint4* src = reinterpret_cast<const uint4*>(p.aux_in + off);
+            pa[0] = __ldg(src);
+            pa[1] = __ldg(src + 1);
+          }
+          if (need_add) {
+            const uint4* src = reinterpret_cast<const uint4*>(p.add_in + off);
+            pd[0] = __ldg(src);
+            pd[1] = __ldg(src + 1);
+          }
+        }
+      };
+      prefetch(half * 16);
 
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + acc * 256;
-      for (int c = 0; c < p.block_n; c += 16) {
+      for (int c = half * 16; c < p.block_n; c += 32) {
         const int col0 = n0 + c;
         if (col0 >= p.N) break;  // warp-uniform
         uint32_t r[16];
         tmem_ld16(taddr + c, r);
+        // operands of this chunk (prefetched) -> locals, then start fetching the next chunk's
+        __align__(16) __nv_bfloat16 ha[16], hd[16];
+        reinterpret_cast<uint4*>(ha)[0] = pa[0];
+        reinterpret_cast<uint4*>(ha)[1] = pa[1];
+        reinterpret_cast<uint4*>(hd)[0] = pd[0];
+        reinterpret_cast<uint4*>(hd)[1] = pd[1];
+        prefetch(c + 32);
         tmem_ld_wait();
         if (!row_ok) continue;
         float v[16];
@@ -255,15 +289,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.0f);
         }
-        if (p.epi_mul != 0) {
+        if (need_aux) {
           float a[16];
           if (full && p.vec_ok) {
-            __align__(16) __nv_bfloat16 h[16];
-            const uint4* src = reinterpret_cast<const uint4*>(p.aux_in + off);
-            reinterpret_cast<uint4*>(h)[0] = __ldg(src);
-            reinterpret_cast<uint4*>(h)[1] = __ldg(src + 1);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) a[i] = bf2f(h[i]);
+            for (int i = 0; i < 16; ++i) a[i] = bf2f(ha[i]);
           } else {
             for (int i = 0; i < 16; ++i) a[i] = (col0 + i < p.N) ? bf2f(p.aux_in[off + i]) : 0.0f;
           }
@@ -280,14 +310,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           for (int i = 0; i < 16; ++i)
             v[i] = drop_keep(p.drop_seed, (uint64_t)(off + i), p.drop_thresh) ? v[i] * p.drop_scale : 0.0f;
         }
-        if (p.add_in != nullptr) {
+        if (need_add) {
           if (full && p.vec_ok) {
-            __align__(16) __nv_bfloat16 h[16];
-            const uint4* src = reinterpret_cast<const uint4*>(p.add_in + off);
-            reinterpret_cast<uint4*>(h)[0] = __ldg(src);
-            reinterpret_cast<uint4*>(h)[1] = __ldg(src + 1);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] += bf2f(h[i]);
+            for (int i = 0; i < 16; ++i) v[i] += bf2f(hd[i]);
           } else {
             for (int i = 0; i < 16; ++i)
               if (col0 + i < p.N) v[i] += bf2f(p.add_in[off + i]);
@@ -393,6 +419,15 @@ static int make_map(CUtensorMap* map, const void* base, uint64_t inner, uint64_t
   }
   return 0;
 }
+
+// ---- optional per-launch timing (bench.py roofline): CUDA events around every gemm_tc_kernel launch
+struct ProfRec {
+  cudaEvent_t e0, e1;
+  long long dims[6];  // M, N, K, batches, a_mn, b_mn
+};
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;
+static size_t g_prof_used = 0;
 
 static int g_num_sms = 0;
 static int g_smem_optin = 0;
@@ -501,7 +536,37 @@ extern "C" int bb_gemm_bf16(const bb_gemm_args* a, void* stream_) {
   const long long total = (long long)p.m_tiles * p.n_tiles * nb1 * nb2 * p.split_k;
   if (total > 0x7fffffffLL) return set_error("bb_gemm_bf16: too many tiles");
   const int grid = total < g_num_sms ? (int)total : g_num_sms;
+  ProfRec* rec = nullptr;
+  if (g_prof_on) {
+    if (g_prof_used == g_prof.size()) {
+      ProfRec r;
+      cudaEventCreate(&r.e0);
+      cudaEventCreate(&r.e1);
+      g_prof.push_back(r);
+    }
+    rec = &g_prof[g_prof_used++];
+    rec->dims[0] = a->M; rec->dims[1] = a->N; rec->dims[2] = a->K; rec->dims[3] = (long long)nb1 * nb2;
+    rec->dims[4] = p.a_mn; rec->dims[5] = p.b_mn;
+    cudaEventRecord(rec->e0, stream);
+  }
   gemm_tc_kernel<<<grid, NUM_THREADS, smem_bytes, stream>>>(ta, tb, p, (int)total);
+  if (rec) cudaEventRecord(rec->e1, stream);
   count_launch();
   return check_launch("gemm_tc_kernel");
+}
+
+extern "C" int bb_gemm_profile(int enable) {
+  bb::g_prof_on = enable != 0;
+  if (enable) bb::g_prof_used = 0;
+  return 0;
+}
+extern "C" int64_t bb_gemm_profile_count(void) { return (int64_t)bb::g_prof_used; }
+extern "C" int bb_gemm_profile_read(int64_t idx, float* ms, int64_t* dims6) {
+  using namespace bb;
+  if (idx < 0 || (size_t)idx >= g_prof_used) return set_error("bb_gemm_profile_read: index out of range");
+  ProfRec& r = g_prof[idx];
+  if (cudaEventSynchronize(r.e1) != cudaSuccess) return set_error("bb_gemm_profile_read: event sync failed");
+  if (cudaEventElapsedTime(ms, r.e0, r.e1) != cudaSuccess) return set_error("bb_gemm_profile_read: elapsed time failed");
+  for (int i = 0; i < 6; ++i) dims6[i] = r.dims[i];
+  return 0;
 }

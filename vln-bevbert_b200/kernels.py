@@ -92,6 +92,23 @@ def gemm(a, b, out, M, N, K, lda, ldb, ldd, a_mn=False, b_mn=False, nb1=1, nb2=1
     return out
 
 
+def gemm_profile(enable: bool):
+    """Start / stop the library's per-launch GEMM timing (CUDA events around every tcgen05 GEMM launch)."""
+    _lib.check(_lib.load().bb_gemm_profile(int(enable)), "bb_gemm_profile")
+
+
+def gemm_profile_records():
+    """[(ms, (M, N, K, batches, a_mn, b_mn)), ...] for the launches recorded since gemm_profile(True)."""
+    lib = _lib.load()
+    out = []
+    ms = C.c_float()
+    dims = (C.c_int64 * 6)()
+    for i in range(int(lib.bb_gemm_profile_count())):
+        _lib.check(lib.bb_gemm_profile_read(i, C.byref(ms), dims), "bb_gemm_profile_read")
+        out.append((float(ms.value), tuple(int(x) for x in dims)))
+    return out
+
+
 # ---------------------------------------------------------------------------------------------- native sub-layers
 def native_sublayers():
     """True: blocks.py hands whole attention / FFN sub-layers to the C++ executors (csrc/layers.cu)."""

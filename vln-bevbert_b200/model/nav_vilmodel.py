@@ -88,7 +88,7 @@ class GlocalTextPathNavCMT(PreTrainedBase):
         local_logits = self.local_sap_head(rt, cand_embeds).view(B, Kc) * (1 - fuse)
         local_logits = local_logits.masked_fill(cand_masks.logical_not(), -float("inf"))
         # bev_cand_vpids[i][0] is the [stop] slot (reference loop skips j == 0)
-        Fm = build_sap_fusion(gmap_vpids, gmap_visited_masks.tolist(), [c[1:] for c in bev_cand_vpids], G, Kc, dev)
+        Fm = build_sap_fusion(gmap_vpids, gmap_visited_masks, [c[1:] for c in bev_cand_vpids], G, Kc, dev)
         fused_logits = global_logits + torch.einsum("bgk,bk->bg", Fm, local_logits.masked_fill(cand_masks.logical_not(), 0.0))
         stop_inf = torch.isinf(local_logits[:, 0])
         if stop_inf.any():

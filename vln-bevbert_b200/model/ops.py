@@ -30,9 +30,11 @@ def build_gmap_segments(traj_step_lens, traj_vp_lens, traj_vpids, traj_cand_vpid
       - the mean over the valid tokens of the panorama of a visited viewpoint, or
       - the mean of the candidate-view tokens (over all panoramas) that point at an unvisited viewpoint;
     row j = 0 ([stop]) and padded rows are empty segments (zeros).  Token (pano p, view v) is row p*Vtot+v of
-    the flattened panorama embeddings.  `traj_vp_lens` is a host list of per-panorama token counts.
+    the flattened panorama embeddings.  The lists come from host strings only; the per-panorama token counts
+    (`traj_vp_lens`, a device tensor) enter through the weights, which are finished on the device
+    (w = [v < len] / len for visited nodes) -- so building them never synchronises with the GPU.
     """
-    seg_off, idx, w = [0], [], []
+    seg_off, idx, w, wpano = [0], [], [], []
     p0 = 0
     for i, P in enumerate(traj_step_lens):
         visited_at = {}
@@ -48,39 +50,61 @@ def build_gmap_segments(traj_step_lens, traj_vp_lens, traj_vpids, traj_cand_vpid
                 vp = nodes[j]
                 if vp in visited_at:
                     pano = visited_at[vp]
-                    n = int(traj_vp_lens[pano])
-                    idx.extend(range(pano * Vtot, pano * Vtot + n))
-                    w.extend([1.0 / n] * n)
+                    idx.extend(range(pano * Vtot, (pano + 1) * Vtot))
+                    w.extend([0.0] * Vtot)               # filled on the device from the token counts
+                    wpano.extend([pano] * Vtot)
                 else:
                     toks = cand_tok[vp]
                     idx.extend(toks)
                     w.extend([1.0 / len(toks)] * len(toks))
+                    wpano.extend([-1] * len(toks))
             seg_off.append(len(idx))
         p0 += P
-    return (torch.tensor(seg_off, dtype=torch.int32, device=device), torch.tensor(idx, dtype=torch.int32, device=device),
-            torch.tensor(w, dtype=torch.float32, device=device))
+    host = torch.tensor([idx, wpano], dtype=torch.int32)
+    wh = torch.tensor(w, dtype=torch.float32)
+    so = torch.tensor(seg_off, dtype=torch.int32)
+    if device.type == "cuda":
+        host, wh, so = host.pin_memory(), wh.pin_memory(), so.pin_memory()
+    dv = host.to(device, non_blocking=True)
+    wd = wh.to(device, non_blocking=True)
+    idx_d, pano_d = dv[0].contiguous(), dv[1].long()
+    lens = traj_vp_lens.to(torch.float32)
+    vis = pano_d >= 0
+    pc = pano_d.clamp(min=0)
+    view = (idx_d.long() - pc * Vtot).to(torch.float32)
+    w_vis = (view < lens[pc]).to(torch.float32) / lens[pc]
+    return so.to(device, non_blocking=True), idx_d, torch.where(vis, w_vis, wd)
 
 
-def build_sap_fusion(gmap_vpids, gmap_visited_masks_host, last_cand_vpids, G, Kc, device):
+def build_sap_fusion(gmap_vpids, gmap_visited_masks, last_cand_vpids, G, Kc, device):
     """(B, G, Kc) 0/1 fp32 matrix F with fused[b,j] = global[b,j] + sum_k F[b,j,k] * local[b,k]
     (pretrain_cmt.py:339-356): slot 0 takes local[0]; an unvisited node takes the local logit of the
-    candidate view that reaches it, otherwise the sum over candidates that lead back to visited nodes."""
+    candidate view that reaches it, otherwise the sum over candidates that lead back to visited nodes.
+    The viewpoint-id matching E[b,j,k] = (node j is candidate k) is host string work; whether a node is
+    visited comes from the device mask, so F is finished on the device without a host synchronisation."""
     B = len(gmap_vpids)
-    F = torch.zeros(B, G, Kc, dtype=torch.float32)
+    E2 = torch.zeros(2, B, G, Kc, dtype=torch.float32)   # [0]: every match, [1]: last candidate per viewpoint
     for i in range(B):
-        visited = {vp for vp, m in zip(gmap_vpids[i], gmap_visited_masks_host[i]) if m}
-        F[i, 0, 0] = 1.0
-        direct, back = {}, []
-        for j, vp in enumerate(last_cand_vpids[i]):
-            if vp in visited:
-                back.append(j + 1)
-            else:
-                direct[vp] = j + 1
-        for j, vp in enumerate(gmap_vpids[i]):
-            if j > 0 and vp not in visited:
-                if vp in direct:
-                    F[i, j, direct[vp]] = 1.0
-                else:
-                    for k in back:
-                        F[i, j, k] = 1.0
-    return F.to(device)
+        pos = {vp: j for j, vp in enumerate(gmap_vpids[i]) if j > 0}
+        last = {}
+        for k, vp in enumerate(last_cand_vpids[i]):
+            j = pos.get(vp)
+            if j is not None and k + 1 < Kc:
+                E2[0, i, j, k + 1] = 1.0
+                last[vp] = (j, k + 1)                     # `tmp[cand_vpid] = ...` overwrites: the last view wins
+        for j, k in last.values():
+            E2[1, i, j, k] = 1.0
+    if device.type == "cuda":
+        E2 = E2.pin_memory()
+    E2 = E2.to(device, non_blocking=True)
+    vis = gmap_visited_masks.to(torch.float32)                     # (B,G)
+    cand_visited = torch.einsum("bgk,bg->bk", E2[0], vis)          # candidate k leads back to a visited node
+    direct = E2[1] * (1.0 - vis)[:, :, None]                       # unvisited node j reached by candidate k
+    has_direct = direct.sum(2, keepdim=True) > 0
+    unvis = (1.0 - vis)
+    unvis[:, 0] = 0.0                                              # slot 0 handled separately
+    F = torch.where(has_direct, direct, cand_visited[:, None, :].expand(B, G, Kc)) * unvis[:, :, None]
+    # padded gmap slots (beyond gmap_len) have no vpid: they only ever get the back-logit term, like the reference
+    F[:, 0, :] = 0.0
+    F[:, 0, 0] = 1.0
+    return F

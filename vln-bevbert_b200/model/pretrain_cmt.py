@@ -210,7 +210,7 @@ class GlocalTextPathCMTPreTraining(PreTrainedBase):
         local_logits = self.local_sap_head(self.rt, cand_embeds).view(B, Kc) * (1 - fuse)
         local_logits = local_logits.masked_fill(cand_masks.logical_not(), -float("inf"))
         # fusion (pretrain_cmt.py:339-356) through a host-built 0/1 matrix; -inf candidates are never selected
-        Fm = build_sap_fusion(gmap_vpids, gmap_visited_masks.tolist(), [c[-1] for c in traj_cand_vpids], G, Kc, dev)
+        Fm = build_sap_fusion(gmap_vpids, gmap_visited_masks, [c[-1] for c in traj_cand_vpids], G, Kc, dev)
         local_fin = local_logits.masked_fill(cand_masks.logical_not(), 0.0)
         fused_logits = global_logits + torch.einsum("bgk,bk->bg", Fm, local_fin)
         stop_inf = torch.isinf(local_logits[:, 0])

@@ -343,7 +343,7 @@ class GlobalMapEncoder(nn.Module):  # :617-700
                              gmap_vpids, gmap_step_ids, gmap_pos_fts, gmap_lens):
         B, G = gmap_step_ids.shape
         nP, Vtot, Hd = traj_embeds.shape
-        seg = build_gmap_segments(traj_step_lens, traj_vp_lens.tolist(), traj_vpids, traj_cand_vpids, gmap_vpids, G,
+        seg = build_gmap_segments(traj_step_lens, traj_vp_lens, traj_vpids, traj_cand_vpids, gmap_vpids, G,
                                   Vtot, traj_embeds.device)
         agg = Bk.run_block(Bk.SegmentSumImpl(), [traj_embeds.reshape(-1, Hd), *seg], []).view(B, G, Hd)
         pos = Bk.run_block(Bk.LinearLNImpl(rt, 1e-12), [gmap_pos_fts],
