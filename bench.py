@@ -237,17 +237,20 @@ def run_ours(args, rank, world, local_rank):
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
     nxt = fetch(0)                                   # prefetch like the reference's PrefetchLoader (data/loader.py:90-125)
-    losses = []
+    losses, prev = [], None
     for i in range(args.steps):
         b, t, ev = nxt
         torch.cuda.current_stream().wait_event(ev)
         if i + 1 < args.steps:
             nxt = fetch(i + 1)
         loss = train_step(b, t)
-        losses.append(loss.item())                   # device -> host read of the step's result
+        if prev is not None:
+            losses.append(prev.item())               # device -> host read of every step's loss, one step late
+        prev = loss.detach()                         # (so the host keeps enqueueing while the GPU finishes the step)
         for v in b.values():
             if torch.is_tensor(v):
                 v.record_stream(torch.cuda.current_stream())
+    losses.append(prev.item())
     e3.record()
     sync_all()
     ms_e2e = e2.elapsed_time(e3)

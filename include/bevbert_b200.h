@@ -178,6 +178,27 @@ int bb_softmax_xent(const float* logits, const int64_t* labels, int64_t rows, in
                     const float* gscale, void* dlogits, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Fused attention scores (keys per row <= 512, head dim 64): the 128 x nk product of one (sample, head, query
+ * tile) goes tcgen05.mma -> TMEM and the row softmax / softmax-backward runs in the epilogue; no fp32 score
+ * matrix in HBM.  A = Q (mode 0) or dO (mode 1): element (b,h,q,d) at A + b*a_s2 + h*a_s1 + q*lda + d;
+ * Bm = K (mode 0) or V (mode 1) likewise with nk rows.  P / Pd / Pin / dS are bf16 (B,H,nq,ldp).
+ *   mode 0: P = softmax(alpha*A Bm^T + kmask + bias), Pd = dropout(P) (Pd may be NULL)
+ *   mode 1: dS = Pin o (g - sum_k Pin g) * out_scale with g = dropout-mask(A Bm^T); dbias (B,nq,nk) f32 += unscaled
+ * Same dropout counters as bb_softmax_fwd/bwd (vilmodel.py:117-127, 335-346).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct bb_attn_scores_args {
+  const void* A; int64_t lda, a_s1, a_s2;
+  const void* Bm; int64_t ldb, b_s1, b_s2;
+  int32_t B, H, nq, nk, ldp, mode;
+  float alpha, out_scale;
+  const float* kmask; const float* bias;
+  uint64_t seed; uint32_t thresh; float scale;
+  void* P; void* Pd;
+  const void* Pin; void* dS; float* dbias;
+} bb_attn_scores_args;
+int bb_attn_scores(const bb_attn_scores_args* args, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Native sub-layer executors: ONE call enqueues the whole kernel sequence of a sub-layer on `stream`.
  *   attention sub-layer = LN(dropout(dense(attention(x, c))) + x)     (vilmodel.py:103-166, 325-363)
  *   FFN sub-layer       = LN(dropout(W2 gelu(W1 a + b1) + b2) + a)     (vilmodel.py:168-193)

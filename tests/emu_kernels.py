@@ -57,6 +57,23 @@ def native_sublayers():
     return False
 
 
+FUSED_SCORES_MAX_KEYS = 512
+
+
+def attn_scores_fwd(q, ldq, k, ldk, B, H, nq, nk, dh, ldp, kmask, bias, drop):
+    S = torch.zeros(B, H, nq, ldp, dtype=F32)
+    gemm(q, k, S, nq, nk, dh, lda=ldq, ldb=ldk, ldd=ldp, nb1=H, nb2=B, a_s=(dh, nq * ldq), b_s=(dh, nk * ldk),
+         d_s=(nq * ldp, H * nq * ldp), alpha=1.0 / math.sqrt(dh))
+    return softmax_fwd(S, kmask, bias, B, H, nq, nk, ldp, drop)
+
+
+def attn_scores_bwd(dctx, ldd, v, ldv, P, B, H, nq, nk, dh, ldp, drop, dbias=None):
+    dP = torch.zeros(B, H, nq, ldp, dtype=F32)
+    gemm(dctx, v, dP, nq, nk, dh, lda=ldd, ldb=ldv, ldd=ldp, nb1=H, nb2=B, a_s=(dh, nq * ldd), b_s=(dh, nk * ldv),
+         d_s=(nq * ldp, H * nq * ldp))
+    return softmax_bwd(P, dP, B, H, nq, nk, ldp, drop, 1.0 / math.sqrt(dh), dbias)
+
+
 def gemm_profile(enable):
     pass
 
@@ -277,7 +294,7 @@ def softmax_xent(logits, labels, V, ld, want_grad=True):
     return loss, dl
 
 
-_NAMES = ["gemm_profile", "gemm_profile_records", "native_sublayers", "attn_desc", "ffn_desc", "sublayer_ws_bytes", "sublayer_fwd", "sublayer_bwd", "gemm", "act_dtype", "drop_params", "launch_count", "reset_launch_count", "bev_lift_index",
+_NAMES = ["attn_scores_fwd", "attn_scores_bwd", "gemm_profile", "gemm_profile_records", "native_sublayers", "attn_desc", "ffn_desc", "sublayer_ws_bytes", "sublayer_fwd", "sublayer_bwd", "gemm", "act_dtype", "drop_params", "launch_count", "reset_launch_count", "bev_lift_index",
           "bev_scatter_mean", "bev_scatter_sem", "cast_to_act", "cast_to_f32", "dropout_act", "layernorm_fwd",
           "layernorm_bwd", "colsum", "softmax_fwd", "softmax_bwd", "embed_sum", "embed_scatter_grad", "gather_rows",
           "scatter_add_rows", "gelu_bwd", "relu_bwd", "add_rows", "scale_rows_", "segment_wsum", "segment_wsum_bwd",

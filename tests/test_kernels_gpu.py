@@ -381,3 +381,38 @@ def test_native_sublayer_executor_equals_python_composition(K, monkeypatch, cros
     assert rel_l2(d2n, d2p) < 1e-5
     for a, b in zip(gn, gp):
         assert rel_l2(a, b) < 1e-4     # split-K / reduction atomics: order-dependent last bits only
+
+
+@pytest.mark.parametrize("nq,nk", [(441, 441), (50, 36), (20, 80), (130, 500)])
+def test_fused_scores_match_unfused_path_and_replay_dropout(K, nq, nk):
+    """bb_attn_scores (softmax / softmax-backward in the tcgen05 epilogue) vs GEMM -> fp32 scores -> softmax kernels:
+    same probabilities, identical dropout mask (same counters), same dS and dbias."""
+    B, H, dh = 2, 12, 64
+    Hd = H * dh
+    ldp = (nk + 7) // 8 * 8
+    q = rnd(B * nq, Hd, scale=0.6).cuda()
+    kv = rnd(B * nk, 2 * Hd, scale=0.6, seed=1).cuda()
+    kmask = torch.zeros(B, nk)
+    kmask[1, nk // 2:] = -10000.0
+    bias = (torch.randn(B, nq, nk) * 0.3)
+    th, sc = K.drop_params(0.1)
+    drop = (4242, th, sc)
+    P, Pd = K.attn_scores_fwd(q, Hd, kv, 2 * Hd, B, H, nq, nk, dh, ldp, dev(kmask), dev(bias), drop)
+    S = torch.empty(B, H, nq, ldp, dtype=torch.float32, device="cuda")
+    K.gemm(q, kv, S, nq, nk, dh, lda=Hd, ldb=2 * Hd, ldd=ldp, nb1=H, nb2=B, a_s=(dh, nq * Hd), b_s=(dh, nk * 2 * Hd),
+           d_s=(nq * ldp, H * nq * ldp), alpha=0.125)
+    P2, Pd2 = K.softmax_fwd(S, dev(kmask), dev(bias), B, H, nq, nk, ldp, drop)
+    assert rel_l2(P, P2) < 4e-3
+    assert float(P.float()[..., nk:].abs().max() if ldp > nk else 0.0) == 0.0
+    big = P2.float() > 1e-3
+    assert torch.equal((Pd.float() != 0)[big], (Pd2.float() != 0)[big]), "dropout masks must coincide"
+    dctx = rnd(B * nq, Hd, seed=2).cuda()
+    v = kv[:, Hd:]
+    db1 = torch.zeros(B, nq, nk, device="cuda")
+    dS = K.attn_scores_bwd(dctx, Hd, v, 2 * Hd, P2, B, H, nq, nk, dh, ldp, drop, db1)
+    dP = torch.empty(B, H, nq, ldp, dtype=torch.float32, device="cuda")
+    K.gemm(dctx, v, dP, nq, nk, dh, lda=Hd, ldb=2 * Hd, ldd=ldp, nb1=H, nb2=B, a_s=(dh, nq * Hd), b_s=(dh, nk * 2 * Hd),
+           d_s=(nq * ldp, H * nq * ldp))
+    db2 = torch.zeros(B, nq, nk, device="cuda")
+    dS2 = K.softmax_bwd(P2, dP, B, H, nq, nk, ldp, drop, 0.125, db2)
+    assert rel_l2(dS, dS2) < 6e-3 and rel_l2(db1, db2) < 1e-4

@@ -36,6 +36,15 @@ class GemmArgs(C.Structure):
     ]
 
 
+class AttnScoresArgs(C.Structure):
+    """struct bb_attn_scores_args (include/bevbert_b200.h)."""
+    _fields_ = [("A", c_void_p), ("lda", c_i64), ("a_s1", c_i64), ("a_s2", c_i64),
+                ("Bm", c_void_p), ("ldb", c_i64), ("b_s1", c_i64), ("b_s2", c_i64)] + \
+        [(n, c_i32) for n in ("B", "H", "nq", "nk", "ldp", "mode")] + [("alpha", c_float), ("out_scale", c_float)] + \
+        [("kmask", c_void_p), ("bias", c_void_p), ("seed", c_u64), ("thresh", c_u32), ("scale", c_float)] + \
+        [(n, c_void_p) for n in ("P", "Pd", "Pin", "dS", "dbias")]
+
+
 class AttnDesc(C.Structure):
     """struct bb_attn_desc (include/bevbert_b200.h)."""
     _fields_ = [(n, c_i32) for n in ("B", "nq", "nk", "Hd", "heads", "cross", "want_dbias")] + [("eps", c_float)] + \
@@ -93,6 +102,7 @@ _SIGNATURES = {
     "bb_segment_wsum_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_int, c_void_p, c_void_p]),
     "bb_add_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_void_p]),
     "bb_axpy_f32_from_bf16": (c_int, [c_void_p, c_void_p, c_i64, c_void_p]),
+    "bb_attn_scores": (c_int, [C.POINTER(AttnScoresArgs), c_void_p]),
     "bb_attn_ws_bytes": (c_int, [C.POINTER(AttnDesc), C.POINTER(c_i64), C.POINTER(c_i64)]),
     "bb_attn_fwd": (c_int, [C.POINTER(AttnDesc), c_void_p]),
     "bb_attn_bwd": (c_int, [C.POINTER(AttnDesc), c_void_p]),

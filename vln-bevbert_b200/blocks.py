@@ -176,11 +176,14 @@ def attn_core_fwd(st, q, ldq, k, ldk, v, ldv, B, H, nq, nk, dh, kmask, bias, dro
     """softmax(Q K^T / sqrt(dh) + kmask + bias) V for every (sample, head).  q/k/v are views whose first
     element is (sample 0, row 0, head 0, dim 0); rows are ld* apart, heads dh apart.  -> ctx (B*nq, H*dh)."""
     ldp = _round8(nk)
-    S = _empty((B, H, nq, ldp), q, torch.float32)
-    K.gemm(q, k, S, nq, nk, dh, lda=ldq, ldb=ldk, ldd=ldp, nb1=H, nb2=B, a_s=(dh, nq * ldq), b_s=(dh, nk * ldk),
-           d_s=(nq * ldp, H * nq * ldp), alpha=1.0 / math.sqrt(dh))
-    P, Pd = K.softmax_fwd(S, kmask, bias, B, H, nq, nk, ldp, drop)
-    del S
+    if nk <= K.FUSED_SCORES_MAX_KEYS and dh == 64:
+        P, Pd = K.attn_scores_fwd(q, ldq, k, ldk, B, H, nq, nk, dh, ldp, kmask, bias, drop)
+    else:
+        S = _empty((B, H, nq, ldp), q, torch.float32)
+        K.gemm(q, k, S, nq, nk, dh, lda=ldq, ldb=ldk, ldd=ldp, nb1=H, nb2=B, a_s=(dh, nq * ldq), b_s=(dh, nk * ldk),
+               d_s=(nq * ldp, H * nq * ldp), alpha=1.0 / math.sqrt(dh))
+        P, Pd = K.softmax_fwd(S, kmask, bias, B, H, nq, nk, ldp, drop)
+        del S
     ctx = _empty((B * nq, H * dh), q)
     K.gemm(Pd, v, ctx, nq, dh, nk, lda=ldp, ldb=ldv, ldd=H * dh, b_mn=True, nb1=H, nb2=B,
            a_s=(nq * ldp, H * nq * ldp), b_s=(dh, nk * ldv), d_s=(dh, nq * H * dh))
@@ -196,12 +199,15 @@ def attn_core_bwd(st, dctx, q, ldq, k, ldk, v, ldv, dq, lddq, dk, lddk, dv, lddv
     # dV = Pd^T dctx
     K.gemm(Pd, dctx, dv, nk, dh, nq, lda=ldp, ldb=HD, ldd=lddv, a_mn=True, b_mn=True, nb1=H, nb2=B,
            a_s=(nq * ldp, H * nq * ldp), b_s=(dh, nq * HD), d_s=(dh, nk * lddv))
-    # dPd = dctx V^T
-    dP = _empty((B, H, nq, ldp), dctx, torch.float32)
-    K.gemm(dctx, v, dP, nq, nk, dh, lda=HD, ldb=ldv, ldd=ldp, nb1=H, nb2=B, a_s=(dh, nq * HD), b_s=(dh, nk * ldv),
-           d_s=(nq * ldp, H * nq * ldp))
-    dS = K.softmax_bwd(P, dP, B, H, nq, nk, ldp, drop, 1.0 / math.sqrt(dh), dbias)
-    del dP
+    if nk <= K.FUSED_SCORES_MAX_KEYS and dh == 64:
+        dS = K.attn_scores_bwd(dctx, HD, v, ldv, P, B, H, nq, nk, dh, ldp, drop, dbias)
+    else:
+        # dPd = dctx V^T
+        dP = _empty((B, H, nq, ldp), dctx, torch.float32)
+        K.gemm(dctx, v, dP, nq, nk, dh, lda=HD, ldb=ldv, ldd=ldp, nb1=H, nb2=B, a_s=(dh, nq * HD), b_s=(dh, nk * ldv),
+               d_s=(nq * ldp, H * nq * ldp))
+        dS = K.softmax_bwd(P, dP, B, H, nq, nk, ldp, drop, 1.0 / math.sqrt(dh), dbias)
+        del dP
     # dQ = dS K ; dK = dS^T Q
     K.gemm(dS, k, dq, nq, dh, nk, lda=ldp, ldb=ldk, ldd=lddq, b_mn=True, nb1=H, nb2=B, a_s=(nq * ldp, H * nq * ldp),
            b_s=(dh, nk * ldk), d_s=(dh, nq * lddq))

@@ -33,7 +33,7 @@ static AttnLayout attn_layout(const bb_attn_desc* d) {
   int64_t o = 0;
   if (!d->cross) { L.qkv = o; o += al(Mq * 3 * Hd * 2); }
   else { L.q = o; o += al(Mq * Hd * 2); L.kv = o; o += al(Mk * 2 * Hd * 2); }
-  L.S = o; o += al(pn * 4);
+  L.S = o; if (d->nk > 512) o += al(pn * 4);   // fp32 scores only on the unfused path
   L.P = o; o += al(pn * 2);
   if (d->th_attn) { L.Pd = o; o += al(pn * 2); } else L.Pd = L.P;
   L.ctx = o; o += al(Mq * Hd * 2);
@@ -47,7 +47,7 @@ static AttnLayout attn_layout(const bb_attn_desc* d) {
   L.dctx = o; o += al(Mq * Hd * 2);
   if (!d->cross) { L.dqkv = o; o += al(Mq * 3 * Hd * 2); }
   else { L.dq = o; o += al(Mq * Hd * 2); L.dkv = o; o += al(Mk * 2 * Hd * 2); }
-  L.dP = o; o += al(pn * 4);
+  L.dP = o; if (d->nk > 512) o += al(pn * 4);
   L.dS = o; o += al(pn * 2);
   L.bwd_bytes = o;
   return L;
@@ -106,6 +106,16 @@ static int attn_core_fwd(const bb_attn_desc* d, const AttnLayout& L, const void*
                          const void* v, int ldv, void* stream) {
   const int B = d->B, H = d->heads, nq = d->nq, nk = d->nk, dh = d->Hd / d->heads, ldp = L.ldp;
   bb_gemm_args g;
+  if (nk <= 512 && dh == 64) {
+    bb_attn_scores_args s;
+    memset(&s, 0, sizeof(s));
+    s.A = q; s.lda = ldq; s.a_s1 = dh; s.a_s2 = (int64_t)nq * ldq;
+    s.Bm = k; s.ldb = ldk; s.b_s1 = dh; s.b_s2 = (int64_t)nk * ldk;
+    s.B = B; s.H = H; s.nq = nq; s.nk = nk; s.ldp = ldp; s.mode = 0; s.alpha = 1.0f / sqrtf((float)dh);
+    s.kmask = d->kmask; s.bias = d->bias; s.seed = d->seed_attn; s.thresh = d->th_attn; s.scale = d->sc_attn;
+    s.P = at(d->ws, L.P); s.Pd = d->th_attn ? at(d->ws, L.Pd) : nullptr;
+    TRY(bb_attn_scores(&s, stream));
+  } else {
   memset(&g, 0, sizeof(g));
   g.A = q; g.B = k; g.D = at(d->ws, L.S); g.M = nq; g.N = nk; g.K = dh; g.nb1 = H; g.nb2 = B;
   g.lda = ldq; g.a_s1 = dh; g.a_s2 = (int64_t)nq * ldq; g.ldb = ldk; g.b_s1 = dh; g.b_s2 = (int64_t)nk * ldk;
@@ -114,6 +124,7 @@ static int attn_core_fwd(const bb_attn_desc* d, const AttnLayout& L, const void*
   TRY(bb_gemm_bf16(&g, stream));
   TRY(bb_softmax_fwd(reinterpret_cast<const float*>(at(d->ws, L.S)), d->kmask, d->bias, B, H, nq, nk, ldp, d->seed_attn,
                      d->th_attn, d->sc_attn, at(d->ws, L.P), d->th_attn ? at(d->ws, L.Pd) : nullptr, stream));
+  }
   memset(&g, 0, sizeof(g));
   g.A = at(d->ws, L.Pd); g.B = v; g.D = at(d->ws, L.ctx); g.M = nq; g.N = dh; g.K = nk; g.nb1 = H; g.nb2 = B;
   g.lda = ldp; g.a_s1 = (int64_t)nq * ldp; g.a_s2 = (int64_t)H * nq * ldp; g.ldb = ldv; g.b_s1 = dh;
@@ -135,6 +146,16 @@ static int attn_core_bwd(const bb_attn_desc* d, const AttnLayout& L, const void*
   g.lda = ldp; g.a_s1 = ps1; g.a_s2 = ps2; g.ldb = HD; g.b_s1 = dh; g.b_s2 = (int64_t)nq * HD;
   g.ldd = lddv; g.d_s1 = dh; g.d_s2 = (int64_t)nk * lddv; g.split_k = 1; g.alpha = 1.0f; g.drop_scale = 1.0f;
   TRY(bb_gemm_bf16(&g, stream));
+  if (nk <= 512 && dh == 64) {
+    bb_attn_scores_args s;
+    memset(&s, 0, sizeof(s));
+    s.A = dctx; s.lda = HD; s.a_s1 = dh; s.a_s2 = (int64_t)nq * HD;
+    s.Bm = v; s.ldb = ldv; s.b_s1 = dh; s.b_s2 = (int64_t)nk * ldv;
+    s.B = B; s.H = H; s.nq = nq; s.nk = nk; s.ldp = ldp; s.mode = 1; s.alpha = 1.0f; s.out_scale = 1.0f / sqrtf((float)dh);
+    s.seed = d->seed_attn; s.thresh = d->th_attn; s.scale = d->sc_attn;
+    s.Pin = at(d->ws, L.P); s.dS = at(d->gws, L.dS); s.dbias = d->want_dbias ? d->dbias : nullptr;
+    TRY(bb_attn_scores(&s, stream));
+  } else {
   // dPd = dctx V^T
   memset(&g, 0, sizeof(g));
   g.A = dctx; g.B = v; g.D = at(d->gws, L.dP); g.M = nq; g.N = nk; g.K = dh; g.nb1 = H; g.nb2 = B;
@@ -144,6 +165,7 @@ static int attn_core_bwd(const bb_attn_desc* d, const AttnLayout& L, const void*
   TRY(bb_softmax_bwd(at(d->ws, L.P), reinterpret_cast<const float*>(at(d->gws, L.dP)), B, H, nq, nk, ldp, d->seed_attn,
                      d->th_attn, d->sc_attn, 1.0f / sqrtf((float)dh), at(d->gws, L.dS), d->want_dbias ? d->dbias : nullptr,
                      stream));
+  }
   // dQ = dS K
   memset(&g, 0, sizeof(g));
   g.A = at(d->gws, L.dS); g.B = k; g.D = dq; g.M = nq; g.N = dh; g.K = nk; g.nb1 = H; g.nb2 = B; g.b_mn = 1;

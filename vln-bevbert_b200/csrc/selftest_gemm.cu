@@ -226,6 +226,11 @@ int main(int argc, char** argv) {
       {"perf_ffn1", 14112, 3072, 768, 1, 1, 0, 0, 768, 0, 0, 768, 0, 0, 3072, 0, 0, 0, 1, 1, 1, 1, 0, 0, 0, 1.f, 20},
       {"perf_ffn2", 14112, 768, 3072, 1, 1, 0, 0, 3072, 0, 0, 3072, 0, 0, 768, 0, 0, 0, 1, 0, 1, 0, 0, 0, 0, 1.f, 20},
       {"perf_sq8k", 8192, 8192, 8192, 1, 1, 0, 0, 8192, 0, 0, 8192, 0, 0, 8192, 0, 0, 0, 1, 0, 0, 0, 0, 0, 256, 1.f, 5},
+      {"perf_lang_ffn1", 2560, 3072, 768, 1, 1, 0, 0, 768, 0, 0, 768, 0, 0, 3072, 0, 0, 0, 1, 1, 1, 1, 0, 0, 0, 1.f, 50},
+      {"perf_lang_dx", 2560, 768, 3072, 1, 1, 0, 1, 3072, 0, 0, 768, 0, 0, 768, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 1.f, 50},
+      {"perf_lang_dw", 3072, 768, 2560, 1, 1, 1, 1, 3072, 0, 0, 768, 0, 0, 768, 0, 0, 1, 1, 0, 0, 0, 0, 0, 128, 1.f, 50},
+      {"perf_attn_s441", 441, 441, 64, 12, 32, 0, 0, 2304, 64, 441LL * 2304, 2304, 64, 441LL * 2304, 448, 441LL * 448,
+       12LL * 441 * 448, 1, 1, 0, 0, 0, 0, 0, 0, 0.125f, 20},
       {"perf_dw", 768, 3072, 14112, 1, 1, 1, 1, 768, 0, 0, 3072, 0, 0, 3072, 0, 0, 1, 8, 0, 0, 0, 0, 0, 0, 1.f, 20},
   };
   if (argc < 2 || !strcmp(argv[1], "list")) {

@@ -143,6 +143,41 @@ def sublayer_bwd(d):
     _lib.check(fn(C.byref(d), _stream()), "bb_sublayer_bwd")
 
 
+FUSED_SCORES_MAX_KEYS = 512
+
+
+def attn_scores_fwd(q, ldq, k, ldk, B, H, nq, nk, dh, ldp, kmask, bias, drop):
+    """fused P = softmax(Q K^T / sqrt(dh) + kmask + bias) (+ dropped copy): -> (P, Pd) bf16 (B,H,nq,ldp)."""
+    lib = _lib.load()
+    a = _lib.AttnScoresArgs()
+    a.A, a.lda, a.a_s1, a.a_s2 = q.data_ptr(), ldq, dh, nq * ldq
+    a.Bm, a.ldb, a.b_s1, a.b_s2 = k.data_ptr(), ldk, dh, nk * ldk
+    a.B, a.H, a.nq, a.nk, a.ldp, a.mode = B, H, nq, nk, ldp, 0
+    a.alpha = 1.0 / (dh ** 0.5)
+    a.kmask, a.bias = _p(kmask), _p(bias)
+    a.seed, a.thresh, a.scale = drop
+    P = torch.empty(B, H, nq, ldp, dtype=BF16, device=q.device)
+    Pd = torch.empty(B, H, nq, ldp, dtype=BF16, device=q.device) if drop[1] else None
+    a.P, a.Pd = P.data_ptr(), _p(Pd)
+    _lib.check(lib.bb_attn_scores(C.byref(a), _stream()), "bb_attn_scores")
+    return P, (Pd if Pd is not None else P)
+
+
+def attn_scores_bwd(dctx, ldd, v, ldv, P, B, H, nq, nk, dh, ldp, drop, dbias=None):
+    """fused dS = P o (g - sum P g) / sqrt(dh), g = dropout-mask(dctx V^T): -> dS bf16 (B,H,nq,ldp)."""
+    lib = _lib.load()
+    a = _lib.AttnScoresArgs()
+    a.A, a.lda, a.a_s1, a.a_s2 = dctx.data_ptr(), ldd, dh, nq * ldd
+    a.Bm, a.ldb, a.b_s1, a.b_s2 = v.data_ptr(), ldv, dh, nk * ldv
+    a.B, a.H, a.nq, a.nk, a.ldp, a.mode = B, H, nq, nk, ldp, 1
+    a.alpha, a.out_scale = 1.0, 1.0 / (dh ** 0.5)
+    a.seed, a.thresh, a.scale = drop
+    dS = torch.empty(B, H, nq, ldp, dtype=BF16, device=dctx.device)
+    a.Pin, a.dS, a.dbias = P.data_ptr(), dS.data_ptr(), _p(dbias)
+    _lib.check(lib.bb_attn_scores(C.byref(a), _stream()), "bb_attn_scores")
+    return dS
+
+
 # ---------------------------------------------------------------------------------------------- BEV
 def bev_lift_index(depths, T_c2w, S_w2c, T_w2c, map_dim, map_res, depth_scale=10.0, fx=7.0, fy=7.0, cx=7.0, cy=7.0,
                    y_clip=0.5, want_pc=False):
