@@ -13,6 +13,7 @@
 #include <mutex>
 #include <vector>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/bevbert_b200.h"
@@ -472,12 +473,16 @@ extern "C" int bb_gemm_bf16(const bb_gemm_args* a, void* stream_) {
   int bn = a->block_n;
   if (bn <= 0) {
     const int gran = p.b_mn ? 64 : 16;
-    if (a->N <= 256) {
+    if (a->N <= 128) {
       bn = ((a->N + gran - 1) / gran) * gran;  // one N tile
     } else {
-      // 256-wide tiles when they still give every SM >= 2 tiles; otherwise 128 for load balance
-      const long long t256 = (long long)p.m_tiles * ((a->N + 255) / 256) * nb1 * nb2 * split_k_req;
-      bn = (t256 >= 2LL * g_num_sms) ? 256 : 128;
+      // The mainloop is latency-bound per k-block (measured ~0.5 us whatever the tile width), so the cost of a
+      // launch is ~ rounds x k-blocks x t(bn) with t(256) ~ 1.3 t(128): pick the width with fewer weighted rounds.
+      const long long per = (long long)p.m_tiles * nb1 * nb2 * split_k_req;
+      const int n256 = (a->N + 255) / 256, n128 = (a->N + 127) / 128;
+      const long long r256 = (per * n256 + g_num_sms - 1) / g_num_sms, r128 = (per * n128 + g_num_sms - 1) / g_num_sms;
+      bn = (13 * r256 <= 10 * r128) ? 256 : 128;
+      if (a->N <= 256 && bn == 256) bn = ((a->N + gran - 1) / gran) * gran;
     }
   }
   if (bn < 16 || bn > 256 || bn % 16 != 0 || (p.b_mn && bn % 64 != 0))
@@ -520,6 +525,14 @@ extern "C" int bb_gemm_bf16(const bb_gemm_args* a, void* stream_) {
   const int stage_bytes = A_STAGE_BYTES + bn * BLOCK_K * 2;
   int stages = (g_smem_optin - 1024 - 512 - 2048) / stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
+  {
+    static int env_stages = -1;  // BB_GEMM_STAGES: pipeline-depth experiments only
+    if (env_stages < 0) {
+      const char* e_ = getenv("BB_GEMM_STAGES");
+      env_stages = e_ ? atoi(e_) : 0;
+    }
+    if (env_stages >= 2 && env_stages < stages) stages = env_stages;
+  }
   if (stages < 2) return set_error("bb_gemm_bf16: not enough shared memory for 2 stages");
   p.stages = stages;
   const size_t smem_bytes = (size_t)stages * stage_bytes + 1024 + 512 + 2048;
