@@ -21,7 +21,8 @@
 
 namespace bb {
 
-constexpr int AS_THREADS = 320;            // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int AS_EPI_WARPS = 16;           // 4 warps per TMEM lane quarter, each owning every 4th 16-column chunk
+constexpr int AS_THREADS = 64 + 32 * AS_EPI_WARPS;  // warp 0 TMA, warp 1 MMA, warps 2..17 epilogue
 constexpr int AS_Q_BYTES = 128 * 64 * 2;   // 16 KB
 constexpr int AS_K_BYTES = 512 * 64 * 2;   // 64 KB
 constexpr int AS_STAGE = AS_Q_BYTES + AS_K_BYTES;
@@ -52,8 +53,8 @@ attn_scores_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   uint64_t* tmem_empty = tmem_full + 1;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty + 1);
   float* skm = reinterpret_cast<float*>(smem + AS_STAGES * AS_STAGE + 256);  // [2][512] key masks
-  float* red_a = skm + 2 * 512;                                              // [2][128]
-  float* red_b = red_a + 2 * 128;                                            // [2][128]
+  float* red_a = skm + 2 * 512;                                              // [4][128] partial max / dot
+  float* red_b = red_a + 4 * 128;                                            // [4][128] partial sum
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -67,7 +68,7 @@ attn_scores_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       mbar_init(&empty_bar[i], 1);
     }
     mbar_init(tmem_full, 1);
-    mbar_init(tmem_empty, 8);
+    mbar_init(tmem_empty, AS_EPI_WARPS);
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -131,10 +132,13 @@ attn_scores_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     }
   } else {
     // ------------------------------------------------------------------ epilogue: row-wise softmax out of TMEM
+    // 16 warps: warp w reads TMEM lanes 32*(w%4)..+31 (one query row per lane) and the 16-column chunks
+    // part, part+4, part+8, ... ; the four parts of a row are combined through shared memory.
     const int quarter = warp & 3;
-    const int half = (warp - 2) >> 2;
-    const int rl = quarter * 32 + lane;  // row within the tile
-    const int e = (warp - 2) * 32 + lane;
+    const int part = (warp - 2) >> 2;     // 0..3
+    const int rl = quarter * 32 + lane;   // row within the tile
+    const int e = (warp - 2) * 32 + lane; // 0..511
+    constexpr int NT = 32 * AS_EPI_WARPS;
     uint32_t tphase = 0;
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
@@ -146,7 +150,7 @@ attn_scores_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       const long long grow = ((long long)b * p.H + h) * p.nq + q;  // global row index of P / dS
       float* km = skm + (it & 1) * 512;
       if (p.mode == 0) {
-        for (int i = e; i < ncols; i += 256)
+        for (int i = e; i < ncols; i += NT)
           km[i] = (i < p.nk) ? (p.kmask ? __ldg(p.kmask + (long long)b * p.nk + i) : 0.0f) : -INFINITY;
       }
       const float* brow = (p.mode == 0 && p.bias && row_ok) ? p.bias + ((long long)b * p.nq + q) * p.nk : nullptr;
@@ -154,60 +158,58 @@ attn_scores_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
 
       mbar_wait(tmem_full, tphase);
       tc_fence_after();
-      asm volatile("bar.sync 1, 256;" ::: "memory");  // key masks visible
+      asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");  // key masks visible
       const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16);
 
       if (p.mode == 0) {
-        // pass 1: row maximum
-        float mx = -INFINITY;
-        for (int c = half * 16; c < ncols; c += 32) {
+        // pass A: online row maximum / sum of exponentials over this warp's chunks
+        float mx = -INFINITY, sum = 0.0f;
+        for (int c = part * 16; c < ncols; c += 64) {
           uint32_t r[16];
           tmem_ld16(taddr + c, r);
           tmem_ld_wait();
+          float sv[16];
+          float cm = -INFINITY;
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            float s = __uint_as_float(r[i]) * p.alpha + km[c + i];
+            float s = fmaf(__uint_as_float(r[i]), p.alpha, km[c + i]);
             if (brow && c + i < p.nk) s += __ldg(brow + c + i);
-            mx = fmaxf(mx, s);
+            sv[i] = s;
+            cm = fmaxf(cm, s);
+          }
+          if (cm > mx) {
+            sum *= __expf(mx - cm);   // exp(-inf) = 0 on the first chunk
+            mx = cm;
+          }
+          if (mx > -INFINITY) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) sum += __expf(sv[i] - mx);
           }
         }
-        red_a[half * 128 + rl] = mx;
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        mx = fmaxf(red_a[rl], red_a[128 + rl]);
-        // pass 2: sum of exponentials
-        float sum = 0.0f;
-        for (int c = half * 16; c < ncols; c += 32) {
+        red_a[part * 128 + rl] = mx;
+        red_b[part * 128 + rl] = sum;
+        asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
+        float m = fmaxf(fmaxf(red_a[rl], red_a[128 + rl]), fmaxf(red_a[256 + rl], red_a[384 + rl]));
+        float l = 0.0f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float mj = red_a[j * 128 + rl];
+          l += (mj > -INFINITY) ? red_b[j * 128 + rl] * __expf(mj - m) : 0.0f;
+        }
+        const float inv = 1.0f / l;     // all keys masked with -inf: 1/0 -> inf, probabilities NaN like torch
+        // pass B: probabilities (and their dropped copy)
+        for (int c = part * 16; c < p.ldp; c += 64) {
           uint32_t r[16];
           tmem_ld16(taddr + c, r);
           tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            float s = __uint_as_float(r[i]) * p.alpha + km[c + i];
-            if (brow && c + i < p.nk) s += __ldg(brow + c + i);
-            sum += __expf(s - mx);
-          }
-        }
-        red_b[half * 128 + rl] = sum;
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        const float inv = 1.0f / (red_b[rl] + red_b[128 + rl]);
-        // pass 3: probabilities (and their dropped copy)
-        for (int c = half * 16; c < p.ldp; c += 32) {
-          float pr[16];
-          if (c < ncols) {
-            uint32_t r[16];
-            tmem_ld16(taddr + c, r);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              float s = __uint_as_float(r[i]) * p.alpha + km[c + i];
-              if (brow && c + i < p.nk) s += __ldg(brow + c + i);
-              pr[i] = (c + i < p.nk) ? __expf(s - mx) * inv : 0.0f;
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) pr[i] = 0.0f;
-          }
           if (!row_ok) continue;
+          float pr[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float s = fmaf(__uint_as_float(r[i]), p.alpha, km[c + i]);
+            if (brow && c + i < p.nk) s += __ldg(brow + c + i);
+            pr[i] = (c + i < p.nk) ? __expf(s - m) * inv : 0.0f;
+          }
           const int nvalid = min(16, p.ldp - c);  // ldp is a multiple of 8: 8 or 16
           __align__(16) __nv_bfloat162 hp[8];
 #pragma unroll
@@ -216,9 +218,11 @@ attn_scores_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           dst[0] = reinterpret_cast<uint4*>(hp)[0];
           if (nvalid == 16) dst[1] = reinterpret_cast<uint4*>(hp)[1];
           if (p.Pd) {
+            if (p.thresh) {
+              const uint64_t base = (uint64_t)(grow * p.ldp + c);
 #pragma unroll
-            for (int i = 0; i < 16; ++i)
-              if (p.thresh) pr[i] = drop_keep(p.seed, (uint64_t)(grow * p.ldp + c + i), p.thresh) ? pr[i] * p.scale : 0.0f;
+              for (int i = 0; i < 16; ++i) pr[i] = drop_keep(p.seed, base + i, p.thresh) ? pr[i] * p.scale : 0.0f;
+            }
 #pragma unroll
             for (int i = 0; i < 8; ++i) hp[i] = __floats2bfloat162_rn(pr[2 * i], pr[2 * i + 1]);
             uint4* dd = reinterpret_cast<uint4*>(p.Pd + grow * p.ldp + c);
@@ -229,7 +233,7 @@ attn_scores_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
       } else {
         // backward: dot = sum_k P g ; dS = P (g - dot) * out_scale
         float dot = 0.0f;
-        for (int c = half * 16; c < ncols; c += 32) {
+        for (int c = part * 16; c < ncols; c += 64) {
           uint32_t r[16];
           tmem_ld16(taddr + c, r);
           __align__(16) __nv_bfloat16 hp[16];
@@ -241,48 +245,44 @@ attn_scores_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
           }
           tmem_ld_wait();
           if (row_ok) {
+            const uint64_t base = (uint64_t)(grow * p.ldp + c);
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
               if (c + i < p.nk) {
                 float g = __uint_as_float(r[i]);
-                if (p.thresh) g = drop_keep(p.seed, (uint64_t)(grow * p.ldp + c + i), p.thresh) ? g * p.scale : 0.0f;
-                dot += __bfloat162float(hp[i]) * g;
+                if (p.thresh) g = drop_keep(p.seed, base + i, p.thresh) ? g * p.scale : 0.0f;
+                dot = fmaf(__bfloat162float(hp[i]), g, dot);
               }
             }
           }
         }
-        red_a[half * 128 + rl] = dot;
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        dot = red_a[rl] + red_a[128 + rl];
-        for (int c = half * 16; c < p.ldp; c += 32) {
-          float ds[16];
+        red_a[part * 128 + rl] = dot;
+        asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
+        dot = (red_a[rl] + red_a[128 + rl]) + (red_a[256 + rl] + red_a[384 + rl]);
+        for (int c = part * 16; c < p.ldp; c += 64) {
           const int nvalid = min(16, p.ldp - c);
-          if (c < ncols) {
-            uint32_t r[16];
-            tmem_ld16(taddr + c, r);
-            __align__(16) __nv_bfloat16 hp[16];
-            if (row_ok) {
-              reinterpret_cast<uint4*>(hp)[0] = __ldg(reinterpret_cast<const uint4*>(prow + c));
-              reinterpret_cast<uint4*>(hp)[1] =
-                  nvalid == 16 ? __ldg(reinterpret_cast<const uint4*>(prow + c) + 1) : make_uint4(0, 0, 0, 0);
-            }
-            tmem_ld_wait();
-            if (!row_ok) continue;
+          uint32_t r[16];
+          tmem_ld16(taddr + c, r);
+          __align__(16) __nv_bfloat16 hp[16];
+          if (row_ok) {
+            reinterpret_cast<uint4*>(hp)[0] = __ldg(reinterpret_cast<const uint4*>(prow + c));
+            reinterpret_cast<uint4*>(hp)[1] =
+                nvalid == 16 ? __ldg(reinterpret_cast<const uint4*>(prow + c) + 1) : make_uint4(0, 0, 0, 0);
+          }
+          tmem_ld_wait();
+          if (!row_ok) continue;
+          float ds[16];
+          const uint64_t base = (uint64_t)(grow * p.ldp + c);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              float d = 0.0f;
-              if (c + i < p.nk) {
-                float g = __uint_as_float(r[i]);
-                if (p.thresh) g = drop_keep(p.seed, (uint64_t)(grow * p.ldp + c + i), p.thresh) ? g * p.scale : 0.0f;
-                d = __bfloat162float(hp[i]) * (g - dot);
-                if (p.dbias) atomicAdd(p.dbias + ((long long)b * p.nq + q) * p.nk + c + i, d);
-              }
-              ds[i] = d * p.out_scale;
+          for (int i = 0; i < 16; ++i) {
+            float d = 0.0f;
+            if (c + i < p.nk) {
+              float g = __uint_as_float(r[i]);
+              if (p.thresh) g = drop_keep(p.seed, base + i, p.thresh) ? g * p.scale : 0.0f;
+              d = __bfloat162float(hp[i]) * (g - dot);
+              if (p.dbias) atomicAdd(p.dbias + ((long long)b * p.nq + q) * p.nk + c + i, d);
             }
-          } else {
-            if (!row_ok) continue;
-#pragma unroll
-            for (int i = 0; i < 16; ++i) ds[i] = 0.0f;
+            ds[i] = d * p.out_scale;
           }
           __align__(16) __nv_bfloat162 ho[8];
 #pragma unroll
@@ -378,7 +378,7 @@ extern "C" int bb_attn_scores(const bb_attn_scores_args* a, void* stream_) {
   if (e) return e;
   const long long total = (long long)p.m_tiles * a->H * a->B;
   const int grid = total < num_sms ? (int)total : num_sms;
-  const size_t smem_bytes = (size_t)AS_STAGES * AS_STAGE + 1024 + 256 + (2 * 512 + 4 * 128) * sizeof(float);
+  const size_t smem_bytes = (size_t)AS_STAGES * AS_STAGE + 1024 + 256 + (2 * 512 + 8 * 128) * sizeof(float);
   attn_scores_kernel<<<grid, AS_THREADS, smem_bytes, stream>>>(ta, tb, p, (int)total);
   count_launch();
   return check_launch("attn_scores_kernel");

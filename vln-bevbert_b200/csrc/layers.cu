@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/bevbert_b200.h"
@@ -16,6 +17,16 @@
 namespace bb {
 
 static inline int64_t al(int64_t n) { return (n + 255) / 256 * 256; }
+// keys-per-row limit of the fused score kernels (BB_FUSED_SCORES_MAX overrides it for experiments; <= 512)
+static inline int fused_max_keys() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("BB_FUSED_SCORES_MAX");
+    v = e ? atoi(e) : 512;
+    if (v > 512) v = 512;
+  }
+  return v;
+}
 static inline int round8(int n) { return (n + 7) / 8 * 8; }
 
 struct AttnLayout {
@@ -33,7 +44,7 @@ static AttnLayout attn_layout(const bb_attn_desc* d) {
   int64_t o = 0;
   if (!d->cross) { L.qkv = o; o += al(Mq * 3 * Hd * 2); }
   else { L.q = o; o += al(Mq * Hd * 2); L.kv = o; o += al(Mk * 2 * Hd * 2); }
-  L.S = o; if (d->nk > 512) o += al(pn * 4);   // fp32 scores only on the unfused path
+  L.S = o; if (d->nk > fused_max_keys()) o += al(pn * 4);   // fp32 scores only on the unfused path
   L.P = o; o += al(pn * 2);
   if (d->th_attn) { L.Pd = o; o += al(pn * 2); } else L.Pd = L.P;
   L.ctx = o; o += al(Mq * Hd * 2);
@@ -47,7 +58,7 @@ static AttnLayout attn_layout(const bb_attn_desc* d) {
   L.dctx = o; o += al(Mq * Hd * 2);
   if (!d->cross) { L.dqkv = o; o += al(Mq * 3 * Hd * 2); }
   else { L.dq = o; o += al(Mq * Hd * 2); L.dkv = o; o += al(Mk * 2 * Hd * 2); }
-  L.dP = o; if (d->nk > 512) o += al(pn * 4);
+  L.dP = o; if (d->nk > fused_max_keys()) o += al(pn * 4);
   L.dS = o; o += al(pn * 2);
   L.bwd_bytes = o;
   return L;
@@ -106,7 +117,7 @@ static int attn_core_fwd(const bb_attn_desc* d, const AttnLayout& L, const void*
                          const void* v, int ldv, void* stream) {
   const int B = d->B, H = d->heads, nq = d->nq, nk = d->nk, dh = d->Hd / d->heads, ldp = L.ldp;
   bb_gemm_args g;
-  if (nk <= 512 && dh == 64) {
+  if (nk <= fused_max_keys() && dh == 64) {
     bb_attn_scores_args s;
     memset(&s, 0, sizeof(s));
     s.A = q; s.lda = ldq; s.a_s1 = dh; s.a_s2 = (int64_t)nq * ldq;
@@ -146,7 +157,7 @@ static int attn_core_bwd(const bb_attn_desc* d, const AttnLayout& L, const void*
   g.lda = ldp; g.a_s1 = ps1; g.a_s2 = ps2; g.ldb = HD; g.b_s1 = dh; g.b_s2 = (int64_t)nq * HD;
   g.ldd = lddv; g.d_s1 = dh; g.d_s2 = (int64_t)nk * lddv; g.split_k = 1; g.alpha = 1.0f; g.drop_scale = 1.0f;
   TRY(bb_gemm_bf16(&g, stream));
-  if (nk <= 512 && dh == 64) {
+  if (nk <= fused_max_keys() && dh == 64) {
     bb_attn_scores_args s;
     memset(&s, 0, sizeof(s));
     s.A = dctx; s.lda = HD; s.a_s1 = dh; s.a_s2 = (int64_t)nq * HD;

@@ -160,14 +160,18 @@ __device__ __forceinline__ float dgelu_erf(float x) {
   return cdf + x * pdf;
 }
 
-// Counter-based RNG for dropout: 32 random bits from (seed, 64-bit element index). Two rounds of a
-// 64-bit mix (splitmix64 finaliser); stateless so backward regenerates the identical mask.
+// Counter-based RNG for dropout: 32 random bits from (seed, 64-bit element index) with a 32-bit avalanche hash
+// (two multiply-xorshift rounds); stateless, so backward regenerates the identical mask.  Kept cheap on purpose:
+// the fused attention epilogue evaluates it once per probability with only a few warps per SM.
 __device__ __forceinline__ uint32_t rng_u32(uint64_t seed, uint64_t idx) {
-  uint64_t z = seed + idx * 0x9E3779B97F4A7C15ull;
-  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  z = z ^ (z >> 31);
-  return static_cast<uint32_t>(z >> 16);
+  uint32_t x = static_cast<uint32_t>(idx) ^ (static_cast<uint32_t>(idx >> 32) * 0x9E3779B1u) ^
+               static_cast<uint32_t>(seed) ^ (static_cast<uint32_t>(seed >> 32) * 0x85EBCA6Bu);
+  x ^= x >> 16;
+  x *= 0x7FEB352Du;
+  x ^= x >> 15;
+  x *= 0x846CA68Bu;
+  x ^= x >> 16;
+  return x;
 }
 // keep element iff rng >= p * 2^32
 __device__ __forceinline__ bool drop_keep(uint64_t seed, uint64_t idx, uint32_t thresh) {

@@ -143,7 +143,7 @@ def sublayer_bwd(d):
     _lib.check(fn(C.byref(d), _stream()), "bb_sublayer_bwd")
 
 
-FUSED_SCORES_MAX_KEYS = 512
+FUSED_SCORES_MAX_KEYS = min(512, int(__import__('os').environ.get('BB_FUSED_SCORES_MAX', '512')))
 
 
 def attn_scores_fwd(q, ldq, k, ldk, B, H, nq, nk, dh, ldp, kmask, bias, drop):
