@@ -112,11 +112,12 @@ int bb_layernorm_fwd(const void* x, int x_f32, const void* residual, const float
                      float* rstd, void* stream);
 /* Backward of the above. dy bf16 (or f32 when dy_f32); recomputes z = dropout(x)+residual.
  * Outputs: dx (bf16, grad wrt x, dropout mask applied) or NULL; dres (bf16, grad wrt residual) or NULL;
- * dgamma/dbeta f32 [H] are ACCUMULATED into (atomics) — caller zeroes them. */
+ * dgamma/dbeta f32 [H] are ACCUMULATED into (atomics) — caller zeroes them.  dxsum f32 [H] (optional) += column
+ * sums of dx: the bias gradient of the dense layer that produced x, without a separate pass. */
 int bb_layernorm_bwd(const void* dy, int dy_f32, const void* x, int x_f32, const void* residual, const float* gamma,
                      const float* mean, const float* rstd, int64_t rows, int H, uint64_t seed_in, uint32_t thresh_in,
                      float scale_in, uint64_t seed_out, uint32_t thresh_out, float scale_out, void* dx, int dx_f32,
-                     void* dres, float* dgamma, float* dbeta, void* stream);
+                     void* dres, float* dgamma, float* dbeta, float* dxsum, void* stream);
 
 /* Column sums of a bf16 (rows, N) matrix accumulated into f32 out[N] (bias gradients). */
 int bb_colsum_bf16(const void* x, int64_t rows, int N, int64_t ld, float* out, void* stream);
@@ -246,6 +247,28 @@ typedef struct bb_ffn_desc {
 int bb_ffn_ws_bytes(const bb_ffn_desc* d, int64_t* fwd_bytes, int64_t* bwd_bytes);
 int bb_ffn_fwd(const bb_ffn_desc* d, void* stream);
 int bb_ffn_bwd(const bb_ffn_desc* d, void* stream);
+
+/* Pre-norm panorama encoder layer (transformer.py:170-182 with nn.MultiheadAttention's packed in_proj):
+ *   x1 = x + drop(out_proj(attention(LN1(x))));  y = x1 + drop(W2 drop(gelu(W1 LN2(x1) + b1)) + b2)
+ * x, y (N*V, Hd) bf16; kmask (N, V) additive (-inf on padding); LayerNorm eps fixed at 1e-5 like nn.LayerNorm. */
+typedef struct bb_pano_desc {
+  int32_t N, V, Hd, heads, Fd;
+  int32_t pad_;
+  const void* x; const float* kmask;
+  const void* w_in; const void* w_out; const void* w1; const void* w2;
+  const float* b_in; const float* b_out; const float* b1; const float* b2;
+  const float* g1; const float* be1; const float* g2; const float* be2;
+  uint64_t seed_attn; uint32_t th_attn; float sc_attn;
+  uint64_t seed1; uint64_t seed2; uint64_t seed3; uint32_t th_h; float sc_h;
+  void* ws; void* y;
+  /* backward only */
+  const void* dy; void* gws; void* dx;
+  float* dw_in; float* db_in; float* dw_out; float* db_out; float* dw1; float* db1; float* dw2; float* db2;
+  float* dg1; float* dbe1; float* dg2; float* dbe2;
+} bb_pano_desc;
+int bb_pano_ws_bytes(const bb_pano_desc* d, int64_t* fwd_bytes, int64_t* bwd_bytes);
+int bb_pano_fwd(const bb_pano_desc* d, void* stream);
+int bb_pano_bwd(const bb_pano_desc* d, void* stream);
 
 #ifdef __cplusplus
 }

@@ -27,14 +27,16 @@ def step(t):
 for i in range(6):
     step(MIX[i % 11])
 torch.cuda.synchronize()
-for label, n in (("wall", 11),):
+for task in ("sap", "mlm", "masksem", "mix"):
+    n = 11
+    torch.cuda.synchronize()
     t0 = time.perf_counter()
     for i in range(n):
-        step(MIX[i % 11])
-    t1 = time.perf_counter()          # host time to ENQUEUE the steps
+        step(MIX[i % 11] if task == "mix" else task)
+    t1 = time.perf_counter()          # host time to ENQUEUE the steps (pure CPU cost when the task has no host sync)
     torch.cuda.synchronize()
     t2 = time.perf_counter()
-    print("host enqueue %.2f ms/step, until GPU idle %.2f ms/step" % ((t1 - t0) / n * 1e3, (t2 - t0) / n * 1e3))
+    print("%-8s host enqueue %.2f ms/step, until GPU idle %.2f ms/step" % (task, (t1 - t0) / n * 1e3, (t2 - t0) / n * 1e3))
 pr = cProfile.Profile()
 pr.enable()
 for i in range(11):

@@ -86,7 +86,7 @@ def _no_native(*a, **k):
     raise RuntimeError("native sub-layer executors are not emulated")
 
 
-attn_desc = ffn_desc = sublayer_ws_bytes = sublayer_fwd = sublayer_bwd = _no_native
+attn_desc = ffn_desc = pano_desc = sublayer_ws_bytes = sublayer_fwd = sublayer_bwd = _no_native
 
 
 def drop_params(p):
@@ -155,7 +155,7 @@ def layernorm_fwd(x, residual, gamma, beta, eps, drop_in=(0, 0, 1.0), drop_out=(
 
 
 def layernorm_bwd(dy, x, residual, gamma, mean, rstd, drop_in=(0, 0, 1.0), drop_out=(0, 0, 1.0), want_dx=True,
-                  want_dres=False, dx_f32=False, dgamma=None, dbeta=None):
+                  want_dres=False, dx_f32=False, dgamma=None, dbeta=None, dxsum=None):
     z = x.to(F32) + (residual.to(F32) if residual is not None else 0)
     xh = (z - mean[:, None]) * rstd[:, None]
     d = dy.to(F32)
@@ -167,6 +167,8 @@ def layernorm_bwd(dy, x, residual, gamma, mean, rstd, drop_in=(0, 0, 1.0), drop_
         dgamma.add_((d * xh).sum(0))
     if dbeta is not None:
         dbeta.add_(d.sum(0))
+    if dxsum is not None:
+        dxsum.add_(dz.sum(0))
     return (dz.clone() if want_dx else None), (dz.clone() if want_dres else None)
 
 
@@ -294,7 +296,7 @@ def softmax_xent(logits, labels, V, ld, want_grad=True):
     return loss, dl
 
 
-_NAMES = ["attn_scores_fwd", "attn_scores_bwd", "gemm_profile", "gemm_profile_records", "native_sublayers", "attn_desc", "ffn_desc", "sublayer_ws_bytes", "sublayer_fwd", "sublayer_bwd", "gemm", "act_dtype", "drop_params", "launch_count", "reset_launch_count", "bev_lift_index",
+_NAMES = ["attn_scores_fwd", "attn_scores_bwd", "gemm_profile", "gemm_profile_records", "native_sublayers", "attn_desc", "ffn_desc", "pano_desc", "sublayer_ws_bytes", "sublayer_fwd", "sublayer_bwd", "gemm", "act_dtype", "drop_params", "launch_count", "reset_launch_count", "bev_lift_index",
           "bev_scatter_mean", "bev_scatter_sem", "cast_to_act", "cast_to_f32", "dropout_act", "layernorm_fwd",
           "layernorm_bwd", "colsum", "softmax_fwd", "softmax_bwd", "embed_sum", "embed_scatter_grad", "gather_rows",
           "scatter_add_rows", "gelu_bwd", "relu_bwd", "add_rows", "scale_rows_", "segment_wsum", "segment_wsum_bwd",

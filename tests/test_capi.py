@@ -29,5 +29,6 @@ def test_gemm_args_struct_layout():
     assert ctypes.sizeof(_lib.GemmArgs) == 216
     # values printed by a C program using sizeof / offsetof on include/bevbert_b200.h
     assert ctypes.sizeof(_lib.AttnDesc) == 280 and _lib.AttnDesc.seed_attn.offset == 128 and _lib.AttnDesc.dbias.offset == 272
+    assert ctypes.sizeof(_lib.PanoDesc) == 320 and _lib.PanoDesc.seed_attn.offset == 136 and _lib.PanoDesc.dbe2.offset == 312
     assert ctypes.sizeof(_lib.FfnDesc) == 184 and _lib.FfnDesc.dbeta.offset == 176
     assert _lib.GemmArgs.block_n.offset == 208 and _lib.GemmArgs.add_in.offset == 200  # == sizeof/offsetof in C

@@ -134,14 +134,16 @@ def test_layernorm_fwd_bwd(K, x_f32, res):
     assert rel_l2(y32, ry) < 1e-5 and rel_l2(y, ry) < 5e-3
     assert rel_l2(mean, rm) < 1e-5 and rel_l2(rstd, rr) < 1e-5
     dg, db = torch.zeros(H).cuda(), torch.zeros(H).cuda()
+    dxs = torch.zeros(H).cuda()
     dx, dres = K.layernorm_bwd(dev(dy), dev(x), dev(r), dev(gam), mean, rstd, want_dres=res, dx_f32=x_f32, dgamma=dg,
-                               dbeta=db)
+                               dbeta=db, dxsum=dxs)
     rdg, rdb = torch.zeros(H), torch.zeros(H)
     rdx, rdres = E.layernorm_bwd(f32(dy), f32(x), f32(r), gam, rm, rr, want_dres=res, dgamma=rdg, dbeta=rdb)
     assert rel_l2(dx, rdx) < (1e-4 if x_f32 else 6e-3)
     if res:
         assert rel_l2(dres, rdres) < 6e-3
     assert rel_l2(dg, rdg) < 1e-4 and rel_l2(db, rdb) < 1e-4
+    assert float((dxs.cpu() - rdx.sum(0)).norm()) < 1e-3 * float(rdx.abs().sum(0).norm())   # bias grad of the dense before LN
 
 
 def test_layernorm_dropout_replay(K):
@@ -416,3 +418,31 @@ def test_fused_scores_match_unfused_path_and_replay_dropout(K, nq, nk):
     db2 = torch.zeros(B, nq, nk, device="cuda")
     dS2 = K.softmax_bwd(P2, dP, B, H, nq, nk, ldp, drop, 0.125, db2)
     assert rel_l2(dS, dS2) < 6e-3 and rel_l2(db1, db2) < 1e-4
+
+
+def test_native_pano_layer_equals_python_composition(K, monkeypatch):
+    import bevbert_b200.blocks as Bk
+    torch.manual_seed(1)
+    N, V, Hd, H, Fd = 7, 36, 768, 12, 3072
+    rt = Bk.Runtime()
+    x = (torch.randn(N, V, Hd) * 0.5).to(BF).cuda()
+    kmask = torch.zeros(N, V).cuda()
+    kmask[2, -9:] = float("-inf")
+    shapes = [(3 * Hd, Hd), (3 * Hd,), (Hd, Hd), (Hd,), (Fd, Hd), (Fd,), (Hd, Fd), (Hd,), (Hd,), (Hd,), (Hd,), (Hd,)]
+    params = [torch.nn.Parameter((torch.randn(*s_) * 0.03).cuda()) for s_ in shapes]
+    for i in (8, 10):
+        params[i].data.add_(1.0)
+    dy = (torch.randn(N, V, Hd) * 0.1).to(BF).cuda()
+    outs = {}
+    for native in (True, False):
+        monkeypatch.setattr(K, "native_sublayers", lambda native=native: native)
+        xi = x.clone().requires_grad_(True)
+        for p_ in params:
+            p_.grad = None
+        rt.begin(True, seed=11)
+        y = Bk.run_block(Bk.PanoLayerImpl(rt, H, 0.1, 0.1), [xi, kmask], params)
+        y.backward(dy)
+        outs[native] = (y.detach().clone(), xi.grad.clone(), [p_.grad.clone() for p_ in params])
+    assert torch.equal(outs[True][0], outs[False][0]) and torch.equal(outs[True][1], outs[False][1])
+    for a, b in zip(outs[True][2], outs[False][2]):
+        assert rel_l2(a, b) < 1e-4

@@ -62,6 +62,17 @@ class FfnDesc(C.Structure):
         [(n, c_void_p) for n in ("ws", "y", "dy", "gws", "da", "dw1", "db1", "dw2", "db2", "dgamma", "dbeta")]
 
 
+class PanoDesc(C.Structure):
+    """struct bb_pano_desc (include/bevbert_b200.h)."""
+    _fields_ = [(n, c_i32) for n in ("N", "V", "Hd", "heads", "Fd", "pad_")] + \
+        [(n, c_void_p) for n in ("x", "kmask", "w_in", "w_out", "w1", "w2", "b_in", "b_out", "b1", "b2", "g1", "be1", "g2",
+                                  "be2")] + \
+        [("seed_attn", c_u64), ("th_attn", c_u32), ("sc_attn", c_float), ("seed1", c_u64), ("seed2", c_u64),
+         ("seed3", c_u64), ("th_h", c_u32), ("sc_h", c_float)] + \
+        [(n, c_void_p) for n in ("ws", "y", "dy", "gws", "dx", "dw_in", "db_in", "dw_out", "db_out", "dw1", "db1", "dw2",
+                                  "db2", "dg1", "dbe1", "dg2", "dbe2")]
+
+
 # name -> (restype, argtypes); mirrors include/bevbert_b200.h one to one
 _SIGNATURES = {
     "bb_last_error": (C.c_char_p, []),
@@ -83,7 +94,7 @@ _SIGNATURES = {
                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "bb_layernorm_bwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_int,
                                  c_u64, c_u32, c_float, c_u64, c_u32, c_float,
-                                 c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+                                 c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "bb_colsum_bf16": (c_int, [c_void_p, c_i64, c_int, c_i64, c_void_p, c_void_p]),
     "bb_softmax_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_u64, c_u32, c_float,
                                c_void_p, c_void_p, c_void_p]),
@@ -109,6 +120,9 @@ _SIGNATURES = {
     "bb_ffn_ws_bytes": (c_int, [C.POINTER(FfnDesc), C.POINTER(c_i64), C.POINTER(c_i64)]),
     "bb_ffn_fwd": (c_int, [C.POINTER(FfnDesc), c_void_p]),
     "bb_ffn_bwd": (c_int, [C.POINTER(FfnDesc), c_void_p]),
+    "bb_pano_ws_bytes": (c_int, [C.POINTER(PanoDesc), C.POINTER(c_i64), C.POINTER(c_i64)]),
+    "bb_pano_fwd": (c_int, [C.POINTER(PanoDesc), c_void_p]),
+    "bb_pano_bwd": (c_int, [C.POINTER(PanoDesc), c_void_p]),
     "bb_softmax_xent": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_i64, c_void_p, c_void_p, c_void_p, c_void_p]),
 }
 

@@ -262,9 +262,8 @@ def attn_sublayer_bwd(st, wc, dy, p, H, want_dbias=False):
     dg, db, dWo, dbo = z[0], z[1], z[2], z[3]
     dbias = z[-1] if want_dbias else None
     dao, dres = K.layernorm_bwd(dy.reshape(-1, Hd), ao, x2, p[8].detach(), st["mean"], st["rstd"], drop_in=st["hdrop"],
-                                want_dres=True, dgamma=dg, dbeta=db)
+                                want_dres=True, dgamma=dg, dbeta=db, dxsum=dbo)
     lin_bwd_dw(dao, ctx, dWo)
-    K.colsum(dao, Hd, out=dbo)
     dctx = lin_bwd_dx(dao, wc.get(p[6]))
     if not cross:
         qkv = st["qkv"]
@@ -309,9 +308,8 @@ def ffn_sublayer_bwd(st, wc, dy, p):
     Fd = hpre.shape[1]
     dg, db, dW2, db2, dW1, db1 = ZeroPool(a.device, (Hd,), (Hd,), (Hd, Fd), (Hd,), (Fd, Hd), (Fd,)).out
     dfo, dres = K.layernorm_bwd(dy, fo, a, p[4].detach(), st["f_mean"], st["f_rstd"], drop_in=st["f_drop"],
-                                want_dres=True, dgamma=dg, dbeta=db)
+                                want_dres=True, dgamma=dg, dbeta=db, dxsum=db2)
     lin_bwd_dw(dfo, h, dW2)
-    K.colsum(dfo, Hd, out=db2)
     dhpre = lin_bwd_dx(dfo, wc.get(p[2]), epi_mul=K.EPI_DGELU, aux_in=hpre)
     lin_bwd_dw(dhpre, a, dW1)
     K.colsum(dhpre, Fd, out=db1)
@@ -503,8 +501,54 @@ class PanoLayerImpl:
     def __init__(self, rt, heads, p_attn=0.0, p_hidden=0.0):
         self.rt, self.wc, self.H, self.pa, self.ph = rt, rt.wc, heads, p_attn, p_hidden
 
+    def _native_fwd(self, st, x, kmask, p):
+        wc, ds = self.wc, self.rt.ds
+        N, V, Hd = x.shape
+        dev = x.device
+        x2 = x.reshape(N * V, Hd)
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
+        w_in, w_out, w1, w2 = wc.get(p[0]), wc.get(p[2]), wc.get(p[4]), wc.get(p[6])
+        d = K.pano_desc()
+        d.N, d.V, d.Hd, d.heads, d.Fd = N, V, Hd, self.H, w1.shape[0]
+        d.x, d.kmask = x2.data_ptr(), (kmask.data_ptr() if kmask is not None else None)
+        d.w_in, d.w_out, d.w1, d.w2 = w_in.data_ptr(), w_out.data_ptr(), w1.data_ptr(), w2.data_ptr()
+        d.b_in, d.b_out, d.b1, d.b2 = p[1].data_ptr(), p[3].data_ptr(), p[5].data_ptr(), p[7].data_ptr()
+        d.g1, d.be1, d.g2, d.be2 = p[8].data_ptr(), p[9].data_ptr(), p[10].data_ptr(), p[11].data_ptr()
+        d.seed_attn, d.th_attn, d.sc_attn = ds.make(self.pa)
+        s1, s2, s3 = ds.make(self.ph), ds.make(self.ph), ds.make(self.ph)
+        d.seed1, d.seed2, d.seed3, d.th_h, d.sc_h = s1[0], s2[0], s3[0], s1[1], s1[2]
+        fb, bb_ = K.sublayer_ws_bytes(d)
+        ws = _ws(fb, dev)
+        y = torch.empty(N * V, Hd, dtype=K.act_dtype(), device=dev)
+        d.ws, d.y = ws.data_ptr(), y.data_ptr()
+        K.sublayer_fwd(d)
+        st.update(p_d=d, p_keep=[x2, kmask, w_in, w_out, w1, w2, ws], p_bwd=bb_, shape=x.shape, Fd=w1.shape[0])
+        return y.view(x.shape)
+
+    def _native_bwd(self, st, dy):
+        d = st["p_d"]
+        N, V, Hd = st["shape"]
+        Fd = st["Fd"]
+        dev = dy.device
+        dy = dy.reshape(-1, Hd)
+        if not dy.is_contiguous():
+            dy = dy.contiguous()
+        z = ZeroPool(dev, (3 * Hd, Hd), (3 * Hd,), (Hd, Hd), (Hd,), (Fd, Hd), (Fd,), (Hd, Fd), (Hd,), (Hd,), (Hd,), (Hd,),
+                     (Hd,)).out
+        gws = _ws(st["p_bwd"], dev)
+        dx = torch.empty(N * V, Hd, dtype=K.act_dtype(), device=dev)
+        d.dy, d.gws, d.dx = dy.data_ptr(), gws.data_ptr(), dx.data_ptr()
+        (d.dw_in, d.db_in, d.dw_out, d.db_out, d.dw1, d.db1, d.dw2, d.db2, d.dg1, d.dbe1, d.dg2, d.dbe2) = \
+            [t.data_ptr() for t in z]
+        K.sublayer_bwd(d)
+        return [dx.view(st["shape"]), None], list(z)
+
     def fwd(self, st, inputs, p):
         x, kmask = inputs
+        st["native"] = K.native_sublayers()
+        if st["native"]:
+            return self._native_fwd(st, x, kmask, p)
         N, V, Hd = x.shape
         dh = Hd // self.H
         x2 = x.reshape(N * V, Hd)
@@ -525,6 +569,8 @@ class PanoLayerImpl:
         return y.view(x.shape)
 
     def bwd(self, st, gouts, p):
+        if st["native"]:
+            return self._native_bwd(st, gouts[0])
         Hd = st["shape"][-1]
         dev = st["x2"].device
         dy = gouts[0].reshape(-1, Hd).contiguous()

@@ -22,7 +22,7 @@ static inline int fused_max_keys() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("BB_FUSED_SCORES_MAX");
-    v = e ? atoi(e) : 512;
+    v = e ? atoi(e) : 0;   // default off: with one CTA per SM the softmax arithmetic has too few warps
     if (v > 512) v = 512;
   }
   return v;
@@ -79,12 +79,12 @@ static int lin_fwd(const void* x, const void* w, void* out, int64_t M, int N, in
 }
 // dx = epi(dy W)
 static int lin_bwd_dx(const void* dy, const void* w, void* out, int64_t M, int N, int Kd, int epi_mul, const void* aux_in,
-                      const void* add_in, void* stream) {
+                      const void* add_in, void* stream, uint64_t seed = 0, uint32_t th = 0, float sc = 1.0f) {
   bb_gemm_args g;
   memset(&g, 0, sizeof(g));
   g.A = dy; g.B = w; g.D = out; g.M = (int32_t)M; g.N = Kd; g.K = N; g.nb1 = 1; g.nb2 = 1;
   g.lda = N; g.ldb = Kd; g.ldd = Kd; g.b_mn = 1; g.alpha = 1.0f; g.epi_mul = epi_mul; g.aux_in = aux_in;
-  g.add_in = add_in; g.split_k = 1; g.drop_scale = 1.0f;
+  g.add_in = add_in; g.split_k = 1; g.drop_seed = seed; g.drop_thresh = th; g.drop_scale = sc;
   return bb_gemm_bf16(&g, stream);
 }
 // dW (N, Kd) += dy^T x   (fp32, zeroed by the caller)
@@ -236,9 +236,8 @@ extern "C" int bb_attn_bwd(const bb_attn_desc* d, void* stream) {
   char* dres = at(d->gws, L.dres);
   TRY(bb_layernorm_bwd(d->dy, 0, at(d->ws, L.ao), 0, d->x, d->gamma, reinterpret_cast<const float*>(at(d->ws, L.mean)),
                        reinterpret_cast<const float*>(at(d->ws, L.rstd)), Mq, Hd, d->seed_h, d->th_h, d->sc_h, 0, 0, 1.0f,
-                       dao, 0, dres, d->dgamma, d->dbeta, stream));
+                       dao, 0, dres, d->dgamma, d->dbeta, d->db_o, stream));
   TRY(lin_bwd_dw(dao, at(d->ws, L.ctx), d->dw_o, Mq, Hd, Hd, stream));
-  TRY(bb_colsum_bf16(dao, Mq, Hd, Hd, d->db_o, stream));
   TRY(lin_bwd_dx(dao, d->w_o, at(d->gws, L.dctx), Mq, Hd, Hd, 0, nullptr, nullptr, stream));
   if (!d->cross) {
     char* qkv = at(d->ws, L.qkv);
@@ -314,11 +313,143 @@ extern "C" int bb_ffn_bwd(const bb_ffn_desc* d, void* stream) {
   char* dhpre = at(d->gws, L.dhpre);
   TRY(bb_layernorm_bwd(d->dy, 0, at(d->ws, L.fo), 0, d->a, d->gamma, reinterpret_cast<const float*>(at(d->ws, L.mean)),
                        reinterpret_cast<const float*>(at(d->ws, L.rstd)), d->M, d->Hd, d->seed_h, d->th_h, d->sc_h, 0, 0,
-                       1.0f, dfo, 0, dres, d->dgamma, d->dbeta, stream));
+                       1.0f, dfo, 0, dres, d->dgamma, d->dbeta, d->db2, stream));
   TRY(lin_bwd_dw(dfo, at(d->ws, L.h), d->dw2, d->M, d->Hd, d->Fd, stream));
-  TRY(bb_colsum_bf16(dfo, d->M, d->Hd, d->Hd, d->db2, stream));
   TRY(lin_bwd_dx(dfo, d->w2, dhpre, d->M, d->Hd, d->Fd, 1, at(d->ws, L.hpre), nullptr, stream));
   TRY(lin_bwd_dw(dhpre, d->a, d->dw1, d->M, d->Fd, d->Hd, stream));
   TRY(bb_colsum_bf16(dhpre, d->M, d->Fd, d->Fd, d->db1, stream));
   return lin_bwd_dx(dhpre, d->w1, d->da, d->M, d->Fd, d->Hd, 0, nullptr, dres, stream);
+}
+
+// ------------------------------------------------------------------------------------------------ panorama layer
+namespace bb {
+struct PanoLayout {
+  AttnLayout A;   // attention-core regions (P, Pd, ctx / dctx, dP, dS) relative to ws / gws
+  int64_t h1, m1, r1, qkv, x1, h2, m2, r2, f, fpre, fwd_bytes;
+  int64_t dy3, dfpre, dh2, dx1ln, dx1, d1g, dqkv, dh1, dxln, bwd_bytes;
+};
+static void pano_attn_desc(const bb_pano_desc* d, bb_attn_desc* a) {
+  memset(a, 0, sizeof(*a));
+  a->B = d->N; a->nq = d->V; a->nk = d->V; a->Hd = d->Hd; a->heads = d->heads;
+  a->kmask = d->kmask; a->seed_attn = d->seed_attn; a->th_attn = d->th_attn; a->sc_attn = d->sc_attn;
+  a->ws = d->ws; a->gws = d->gws;
+}
+static PanoLayout pano_layout(const bb_pano_desc* d) {
+  PanoLayout L;
+  memset(&L, 0, sizeof(L));
+  const int64_t M = (int64_t)d->N * d->V, Hd = d->Hd, Fd = d->Fd;
+  const int ldp = round8(d->V);
+  const int64_t pn = (int64_t)d->N * d->heads * d->V * ldp;
+  const bool fused = d->V <= fused_max_keys() && Hd / d->heads == 64;
+  int64_t o = 0;
+  L.h1 = o; o += al(M * Hd * 2);
+  L.m1 = o; o += al(M * 4);
+  L.r1 = o; o += al(M * 4);
+  L.qkv = o; o += al(M * 3 * Hd * 2);
+  L.A.ldp = ldp;
+  L.A.S = o; if (!fused) o += al(pn * 4);
+  L.A.P = o; o += al(pn * 2);
+  if (d->th_attn) { L.A.Pd = o; o += al(pn * 2); } else L.A.Pd = L.A.P;
+  L.A.ctx = o; o += al(M * Hd * 2);
+  L.x1 = o; o += al(M * Hd * 2);
+  L.h2 = o; o += al(M * Hd * 2);
+  L.m2 = o; o += al(M * 4);
+  L.r2 = o; o += al(M * 4);
+  L.f = o; o += al(M * Fd * 2);
+  L.fpre = o; o += al(M * Fd * 2);
+  L.fwd_bytes = o;
+  o = 0;
+  L.dy3 = o; o += al(M * Hd * 2);
+  L.dfpre = o; o += al(M * Fd * 2);
+  L.dh2 = o; o += al(M * Hd * 2);
+  L.dx1ln = o; o += al(M * Hd * 2);
+  L.dx1 = o; o += al(M * Hd * 2);
+  L.d1g = o; o += al(M * Hd * 2);
+  L.A.dctx = o; o += al(M * Hd * 2);
+  L.dqkv = o; o += al(M * 3 * Hd * 2);
+  L.A.dP = o; if (!fused) o += al(pn * 4);
+  L.A.dS = o; o += al(pn * 2);
+  L.dh1 = o; o += al(M * Hd * 2);
+  L.dxln = o; o += al(M * Hd * 2);
+  L.bwd_bytes = o;
+  return L;
+}
+}  // namespace bb
+
+extern "C" int bb_pano_ws_bytes(const bb_pano_desc* d, int64_t* fwd_bytes, int64_t* bwd_bytes) {
+  if (!d) return set_error("bb_pano_ws_bytes: null descriptor");
+  const PanoLayout L = pano_layout(d);
+  if (fwd_bytes) *fwd_bytes = L.fwd_bytes;
+  if (bwd_bytes) *bwd_bytes = L.bwd_bytes;
+  return 0;
+}
+
+extern "C" int bb_pano_fwd(const bb_pano_desc* d, void* stream) {
+  if (!d || !d->x || !d->ws || !d->y) return set_error("bb_pano_fwd: null argument");
+  const PanoLayout L = pano_layout(d);
+  const int Hd = d->Hd, Fd = d->Fd;
+  const int64_t M = (int64_t)d->N * d->V;
+  bb_attn_desc a;
+  pano_attn_desc(d, &a);
+  char* qkv = at(d->ws, L.qkv);
+  TRY(bb_layernorm_fwd(d->x, 0, nullptr, d->g1, d->be1, 1e-5f, M, Hd, 0, 0, 1.0f, 0, 0, 1.0f, at(d->ws, L.h1), nullptr,
+                       reinterpret_cast<float*>(at(d->ws, L.m1)), reinterpret_cast<float*>(at(d->ws, L.r1)), stream));
+  TRY(lin_fwd(at(d->ws, L.h1), d->w_in, qkv, M, 3 * Hd, Hd, d->b_in, 0, nullptr, 0, 0, 1.0f, nullptr, 0, stream));
+  TRY(attn_core_fwd(&a, L.A, qkv, 3 * Hd, qkv + (int64_t)Hd * 2, 3 * Hd, qkv + (int64_t)2 * Hd * 2, 3 * Hd, stream));
+  TRY(lin_fwd(at(d->ws, L.A.ctx), d->w_out, at(d->ws, L.x1), M, Hd, Hd, d->b_out, 0, nullptr, d->seed1, d->th_h, d->sc_h,
+              d->x, 0, stream));
+  TRY(bb_layernorm_fwd(at(d->ws, L.x1), 0, nullptr, d->g2, d->be2, 1e-5f, M, Hd, 0, 0, 1.0f, 0, 0, 1.0f, at(d->ws, L.h2),
+                       nullptr, reinterpret_cast<float*>(at(d->ws, L.m2)), reinterpret_cast<float*>(at(d->ws, L.r2)),
+                       stream));
+  TRY(lin_fwd(at(d->ws, L.h2), d->w1, at(d->ws, L.f), M, Fd, Hd, d->b1, 1, at(d->ws, L.fpre), d->seed2, d->th_h, d->sc_h,
+              nullptr, 0, stream));
+  return lin_fwd(at(d->ws, L.f), d->w2, d->y, M, Hd, Fd, d->b2, 0, nullptr, d->seed3, d->th_h, d->sc_h, at(d->ws, L.x1), 0,
+                 stream);
+}
+
+extern "C" int bb_pano_bwd(const bb_pano_desc* d, void* stream) {
+  if (!d || !d->x || !d->ws || !d->gws || !d->dy || !d->dx) return set_error("bb_pano_bwd: null argument");
+  const PanoLayout L = pano_layout(d);
+  const int Hd = d->Hd, Fd = d->Fd;
+  const int64_t M = (int64_t)d->N * d->V;
+  bb_attn_desc a;
+  pano_attn_desc(d, &a);
+  // y = x1 + drop3(f W2^T + b2)
+  const void* dy3 = d->dy;
+  if (d->th_h) {
+    TRY(bb_dropout_bf16(d->dy, at(d->gws, L.dy3), M * Hd, d->seed3, d->th_h, d->sc_h, stream));
+    dy3 = at(d->gws, L.dy3);
+  }
+  TRY(lin_bwd_dw(dy3, at(d->ws, L.f), d->dw2, M, Hd, Fd, stream));
+  TRY(bb_colsum_bf16(dy3, M, Hd, Hd, d->db2, stream));
+  TRY(lin_bwd_dx(dy3, d->w2, at(d->gws, L.dfpre), M, Hd, Fd, 1, at(d->ws, L.fpre), nullptr, stream, d->seed2, d->th_h,
+                 d->sc_h));
+  TRY(lin_bwd_dw(at(d->gws, L.dfpre), at(d->ws, L.h2), d->dw1, M, Fd, Hd, stream));
+  TRY(bb_colsum_bf16(at(d->gws, L.dfpre), M, Fd, Fd, d->db1, stream));
+  TRY(lin_bwd_dx(at(d->gws, L.dfpre), d->w1, at(d->gws, L.dh2), M, Fd, Hd, 0, nullptr, nullptr, stream));
+  TRY(bb_layernorm_bwd(at(d->gws, L.dh2), 0, at(d->ws, L.x1), 0, nullptr, d->g2,
+                       reinterpret_cast<const float*>(at(d->ws, L.m2)), reinterpret_cast<const float*>(at(d->ws, L.r2)), M,
+                       Hd, 0, 0, 1.0f, 0, 0, 1.0f, at(d->gws, L.dx1ln), 0, nullptr, d->dg2, d->dbe2, nullptr, stream));
+  TRY(bb_add_bf16(at(d->gws, L.dx1ln), d->dy, at(d->gws, L.dx1), M * Hd, stream));
+  // x1 = x + drop1(ctx Wo^T + bo)
+  const void* d1g = at(d->gws, L.dx1);
+  if (d->th_h) {
+    TRY(bb_dropout_bf16(at(d->gws, L.dx1), at(d->gws, L.d1g), M * Hd, d->seed1, d->th_h, d->sc_h, stream));
+    d1g = at(d->gws, L.d1g);
+  }
+  TRY(lin_bwd_dw(d1g, at(d->ws, L.A.ctx), d->dw_out, M, Hd, Hd, stream));
+  TRY(bb_colsum_bf16(d1g, M, Hd, Hd, d->db_out, stream));
+  TRY(lin_bwd_dx(d1g, d->w_out, at(d->gws, L.A.dctx), M, Hd, Hd, 0, nullptr, nullptr, stream));
+  char* qkv = at(d->ws, L.qkv);
+  char* dqkv = at(d->gws, L.dqkv);
+  const int Lq = 3 * Hd;
+  TRY(attn_core_bwd(&a, L.A, qkv, Lq, qkv + (int64_t)Hd * 2, Lq, qkv + (int64_t)2 * Hd * 2, Lq, dqkv, Lq,
+                    dqkv + (int64_t)Hd * 2, Lq, dqkv + (int64_t)2 * Hd * 2, Lq, stream));
+  TRY(lin_bwd_dw(dqkv, at(d->ws, L.h1), d->dw_in, M, 3 * Hd, Hd, stream));
+  TRY(bb_colsum_bf16(dqkv, M, 3 * Hd, 3 * Hd, d->db_in, stream));
+  TRY(lin_bwd_dx(dqkv, d->w_in, at(d->gws, L.dh1), M, 3 * Hd, Hd, 0, nullptr, nullptr, stream));
+  TRY(bb_layernorm_bwd(at(d->gws, L.dh1), 0, d->x, 0, nullptr, d->g1, reinterpret_cast<const float*>(at(d->ws, L.m1)),
+                       reinterpret_cast<const float*>(at(d->ws, L.r1)), M, Hd, 0, 0, 1.0f, 0, 0, 1.0f, at(d->gws, L.dxln), 0,
+                       nullptr, d->dg1, d->dbe1, nullptr, stream));
+  return bb_add_bf16(at(d->gws, L.dxln), at(d->gws, L.dx1), d->dx, M * Hd, stream);
 }

@@ -300,14 +300,15 @@ layernorm_bwd_kernel(const DYT* __restrict__ dy, const XT* __restrict__ x, const
                      const float* __restrict__ gamma, const float* __restrict__ mean_in,
                      const float* __restrict__ rstd_in, long long rows, int H, uint64_t seed_in, uint32_t thresh_in,
                      float scale_in, uint64_t seed_out, uint32_t thresh_out, float scale_out, DXT* __restrict__ dx,
-                     bf16* __restrict__ dres, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+                     bf16* __restrict__ dres, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                     float* __restrict__ dxsum) {
   extern __shared__ float ln_part[];  // [2][LN_WARPS][H] per-warp partial dgamma / dbeta (no atomics, no conflicts)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float pg[LN_MAXCH][8], pb[LN_MAXCH][8];
+  float pg[LN_MAXCH][8], pb[LN_MAXCH][8], px[LN_MAXCH][8];
 #pragma unroll
   for (int c = 0; c < LN_MAXCH; ++c)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) pg[c][j] = pb[c][j] = 0.f;
+    for (int j = 0; j < 8; ++j) pg[c][j] = pb[c][j] = px[c][j] = 0.f;
 
   for (long long row = blockIdx.x * (long long)LN_WARPS + warp; row < rows; row += (long long)gridDim.x * LN_WARPS) {
     const long long base = row * H;
@@ -354,37 +355,43 @@ layernorm_bwd_kernel(const DYT* __restrict__ dy, const XT* __restrict__ x, const
 #pragma unroll
         for (int j = 0; j < 8; ++j) dz[j] = rstd * (g[c][j] - c1 - xh[c][j] * c2);
         if (dres) store8(dres + base + col, dz);
-        if (dx) {
+        if (dx || dxsum) {
           if (thresh_in) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) dz[j] = drop_keep(seed_in, base + col + j, thresh_in) ? dz[j] * scale_in : 0.f;
           }
-          store8(dx + base + col, dz);
+          if (dx) store8(dx + base + col, dz);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) px[c][j] += dz[j];
         }
       }
     }
   }
-  if (dgamma || dbeta) {
+  if (dgamma || dbeta || dxsum) {
     float* sg = ln_part;
     float* sb = ln_part + LN_WARPS * H;
+    float* sx = ln_part + 2 * LN_WARPS * H;
 #pragma unroll
     for (int c = 0; c < LN_MAXCH; ++c) {
       const int col = c * 256 + lane * 8;
       if (col < H) {
         store8(sg + warp * H + col, pg[c]);
         store8(sb + warp * H + col, pb[c]);
+        store8(sx + warp * H + col, px[c]);
       }
     }
     __syncthreads();
     for (int i = threadIdx.x; i < H; i += blockDim.x) {
-      float a = 0.f, b = 0.f;
+      float a = 0.f, b = 0.f, x_ = 0.f;
 #pragma unroll
       for (int w = 0; w < LN_WARPS; ++w) {
         a += sg[w * H + i];
         b += sb[w * H + i];
+        x_ += sx[w * H + i];
       }
       if (dgamma) atomicAdd(dgamma + i, a);
       if (dbeta) atomicAdd(dbeta + i, b);
+      if (dxsum) atomicAdd(dxsum + i, x_);
     }
   }
 }
@@ -745,29 +752,29 @@ extern "C" int bb_layernorm_bwd(const void* dy, int dy_f32, const void* x, int x
                                 const float* gamma, const float* mean, const float* rstd, int64_t rows, int H,
                                 uint64_t seed_in, uint32_t thresh_in, float scale_in, uint64_t seed_out,
                                 uint32_t thresh_out, float scale_out, void* dx, int dx_f32, void* dres, float* dgamma,
-                                float* dbeta, void* stream) {
+                                float* dbeta, float* dxsum, void* stream) {
   if (rows <= 0) return 0;
   if (H % 8 != 0 || H > LN_MAXCH * 256) return set_error("bb_layernorm_bwd: H must be a multiple of 8 and <= 1024");
   long long g = (rows + LN_WARPS - 1) / LN_WARPS;
   if (g > 148 * 2) g = 148 * 2;
   const unsigned grid = (unsigned)g;
-  const size_t ln_smem = (size_t)2 * LN_WARPS * H * sizeof(float);
+  const size_t ln_smem = (size_t)3 * LN_WARPS * H * sizeof(float);
   {
     static bool attr_done = false;
     if (!attr_done) {
-      cudaFuncSetAttribute(layernorm_bwd_kernel<bf16, bf16, bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
-      cudaFuncSetAttribute(layernorm_bwd_kernel<bf16, float, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
-      cudaFuncSetAttribute(layernorm_bwd_kernel<float, bf16, bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
-      cudaFuncSetAttribute(layernorm_bwd_kernel<float, float, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
-      cudaFuncSetAttribute(layernorm_bwd_kernel<bf16, bf16, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
-      cudaFuncSetAttribute(layernorm_bwd_kernel<bf16, float, bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
+      cudaFuncSetAttribute(layernorm_bwd_kernel<bf16, bf16, bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304);
+      cudaFuncSetAttribute(layernorm_bwd_kernel<bf16, float, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304);
+      cudaFuncSetAttribute(layernorm_bwd_kernel<float, bf16, bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304);
+      cudaFuncSetAttribute(layernorm_bwd_kernel<float, float, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304);
+      cudaFuncSetAttribute(layernorm_bwd_kernel<bf16, bf16, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304);
+      cudaFuncSetAttribute(layernorm_bwd_kernel<bf16, float, bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304);
       attr_done = true;
     }
   }
 #define LN_BWD(DYT, XT, DXT)                                                                                        \
   layernorm_bwd_kernel<DYT, XT, DXT><<<grid, LN_WARPS * 32, ln_smem, STREAM>>>(                                     \
       (const DYT*)dy, (const XT*)x, (const bf16*)residual, gamma, mean, rstd, rows, H, seed_in, thresh_in, scale_in, \
-      seed_out, thresh_out, scale_out, (DXT*)dx, (bf16*)dres, dgamma, dbeta)
+      seed_out, thresh_out, scale_out, (DXT*)dx, (bf16*)dres, dgamma, dbeta, dxsum)
   if (!dy_f32 && !x_f32 && !dx_f32) LN_BWD(bf16, bf16, bf16);
   else if (!dy_f32 && x_f32 && dx_f32) LN_BWD(bf16, float, float);
   else if (dy_f32 && !x_f32 && !dx_f32) LN_BWD(float, bf16, bf16);

@@ -123,27 +123,31 @@ def ffn_desc():
     return _lib.FfnDesc()
 
 
+def pano_desc():
+    return _lib.PanoDesc()
+
+
 def sublayer_ws_bytes(d):
     lib = _lib.load()
     f, b = C.c_int64(), C.c_int64()
-    fn = lib.bb_attn_ws_bytes if isinstance(d, _lib.AttnDesc) else lib.bb_ffn_ws_bytes
+    fn = {_lib.AttnDesc: lib.bb_attn_ws_bytes, _lib.FfnDesc: lib.bb_ffn_ws_bytes, _lib.PanoDesc: lib.bb_pano_ws_bytes}[type(d)]
     _lib.check(fn(C.byref(d), C.byref(f), C.byref(b)), "bb_*_ws_bytes")
     return f.value, b.value
 
 
 def sublayer_fwd(d):
     lib = _lib.load()
-    fn = lib.bb_attn_fwd if isinstance(d, _lib.AttnDesc) else lib.bb_ffn_fwd
+    fn = {_lib.AttnDesc: lib.bb_attn_fwd, _lib.FfnDesc: lib.bb_ffn_fwd, _lib.PanoDesc: lib.bb_pano_fwd}[type(d)]
     _lib.check(fn(C.byref(d), _stream()), "bb_sublayer_fwd")
 
 
 def sublayer_bwd(d):
     lib = _lib.load()
-    fn = lib.bb_attn_bwd if isinstance(d, _lib.AttnDesc) else lib.bb_ffn_bwd
+    fn = {_lib.AttnDesc: lib.bb_attn_bwd, _lib.FfnDesc: lib.bb_ffn_bwd, _lib.PanoDesc: lib.bb_pano_bwd}[type(d)]
     _lib.check(fn(C.byref(d), _stream()), "bb_sublayer_bwd")
 
 
-FUSED_SCORES_MAX_KEYS = min(512, int(__import__('os').environ.get('BB_FUSED_SCORES_MAX', '512')))
+FUSED_SCORES_MAX_KEYS = min(512, int(__import__('os').environ.get('BB_FUSED_SCORES_MAX', '0')))
 
 
 def attn_scores_fwd(q, ldq, k, ldk, B, H, nq, nk, dh, ldp, kmask, bias, drop):
@@ -272,8 +276,8 @@ def layernorm_fwd(x, residual, gamma, beta, eps, drop_in=(0, 0, 1.0), drop_out=(
 
 
 def layernorm_bwd(dy, x, residual, gamma, mean, rstd, drop_in=(0, 0, 1.0), drop_out=(0, 0, 1.0), want_dx=True,
-                  want_dres=False, dx_f32=False, dgamma=None, dbeta=None):
-    """-> (dx | None, dres | None); dgamma/dbeta f32 [H] are accumulated into."""
+                  want_dres=False, dx_f32=False, dgamma=None, dbeta=None, dxsum=None):
+    """-> (dx | None, dres | None); dgamma/dbeta/dxsum f32 [H] are accumulated into (dxsum = column sums of dx)."""
     lib = _lib.load()
     rows, H = x.shape
     dev = x.device
@@ -283,7 +287,7 @@ def layernorm_bwd(dy, x, residual, gamma, mean, rstd, drop_in=(0, 0, 1.0), drop_
                                     int(x.dtype == torch.float32), _p(residual), gamma.data_ptr(), mean.data_ptr(),
                                     rstd.data_ptr(), rows, H, drop_in[0], drop_in[1], drop_in[2], drop_out[0],
                                     drop_out[1], drop_out[2], _p(dx), int(dx_f32), _p(dres), _p(dgamma), _p(dbeta),
-                                    _stream()), "bb_layernorm_bwd")
+                                    _p(dxsum), _stream()), "bb_layernorm_bwd")
     return dx, dres
 
 
