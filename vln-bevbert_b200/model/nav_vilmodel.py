@@ -90,9 +90,8 @@ class GlocalTextPathNavCMT(PreTrainedBase):
         # bev_cand_vpids[i][0] is the [stop] slot (reference loop skips j == 0)
         Fm = build_sap_fusion(gmap_vpids, gmap_visited_masks, [c[1:] for c in bev_cand_vpids], G, Kc, dev)
         fused_logits = global_logits + torch.einsum("bgk,bk->bg", Fm, local_logits.masked_fill(cand_masks.logical_not(), 0.0))
-        stop_inf = torch.isinf(local_logits[:, 0])
-        if stop_inf.any():
-            fused_logits[:, 0] = torch.where(stop_inf, local_logits[:, 0], fused_logits[:, 0])
+        fused_logits = torch.cat([torch.where(torch.isinf(local_logits[:, :1]), local_logits[:, :1], fused_logits[:, :1]),
+                                  fused_logits[:, 1:]], 1)
         obj_logits = None
         if obj_out is not None:
             obj_logits = self.og_head(rt, obj_out.contiguous()).squeeze(2).masked_fill(obj_masks.logical_not(), -float("inf"))

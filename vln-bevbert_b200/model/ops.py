@@ -63,8 +63,23 @@ def build_gmap_segments(traj_step_lens, traj_vp_lens, traj_vpids, traj_cand_vpid
     host = torch.tensor([idx, wpano], dtype=torch.int32)
     wh = torch.tensor(w, dtype=torch.float32)
     so = torch.tensor(seg_off, dtype=torch.int32)
+    return finish_gmap_segments((host, wh, so), traj_vp_lens, Vtot, device)
+
+
+def host_gmap_segments(traj_step_lens, traj_vpids, traj_cand_vpids, gmap_vpids, G, Vtot):
+    """The host half of build_gmap_segments (string matching only) -- can run in the data loader / collate."""
+    seg = build_gmap_segments(traj_step_lens, None, traj_vpids, traj_cand_vpids, gmap_vpids, G, Vtot, None)
+    return seg
+
+
+def finish_gmap_segments(host_parts, traj_vp_lens, Vtot, device):
+    """Device half: upload the host lists (pinned, non-blocking) and finish the visited-node weights from the
+    per-panorama token counts."""
+    host, wh, so = host_parts
+    if device is None:
+        return host_parts
     if device.type == "cuda":
-        host, wh, so = host.pin_memory(), wh.pin_memory(), so.pin_memory()
+        host, wh, so = [t if t.is_pinned() else t.pin_memory() for t in (host, wh, so)]
     dv = host.to(device, non_blocking=True)
     wd = wh.to(device, non_blocking=True)
     idx_d, pano_d = dv[0].contiguous(), dv[1].long()
@@ -76,14 +91,37 @@ def build_gmap_segments(traj_step_lens, traj_vp_lens, traj_vpids, traj_cand_vpid
     return so.to(device, non_blocking=True), idx_d, torch.where(vis, w_vis, wd)
 
 
-def build_sap_fusion(gmap_vpids, gmap_visited_masks, last_cand_vpids, G, Kc, device):
-    """(B, G, Kc) 0/1 fp32 matrix F with fused[b,j] = global[b,j] + sum_k F[b,j,k] * local[b,k]
-    (pretrain_cmt.py:339-356): slot 0 takes local[0]; an unvisited node takes the local logit of the
-    candidate view that reaches it, otherwise the sum over candidates that lead back to visited nodes.
-    The viewpoint-id matching E[b,j,k] = (node j is candidate k) is host string work; whether a node is
-    visited comes from the device mask, so F is finished on the device without a host synchronisation."""
+class PreparedList(list):
+    """A host id list that carries index tensors precomputed from it (see prepare_batch)."""
+    host_segments = None
+    host_fusion = None
+
+
+def prepare_batch(batch):
+    """Optional collate-time step (the reference's `sap_collate` / `mlm_collate` run in DataLoader workers,
+    pretrain_src/data/tasks.py:118-160): does the string matching behind the topological-map aggregation and the
+    SAP logit fusion once, on the host, into pinned index tensors attached to `batch['gmap_vpids']`.  forward()
+    finds and uses them; without this call it builds the same tensors itself (same results, more host time
+    inside the step)."""
+    gv = PreparedList(batch["gmap_vpids"])
+    G = batch["gmap_step_ids"].shape[1]
+    Vtot = batch["traj_loc_fts"].shape[1]
+    parts = host_gmap_segments(batch["traj_step_lens"], batch["traj_vpids"], batch["traj_cand_vpids"], gv, G, Vtot)
+    pin = torch.cuda.is_available()
+    gv.host_segments = ((G, Vtot), tuple(t.pin_memory() if pin else t for t in parts))
+    if "bev_cand_idxs" in batch:
+        Kc = batch["bev_cand_idxs"].shape[1]
+        E2 = _fusion_matches(gv, [c[-1] for c in batch["traj_cand_vpids"]], G, Kc)
+        gv.host_fusion = ((G, Kc), E2.pin_memory() if pin else E2)
+    out = dict(batch)
+    out["gmap_vpids"] = gv
+    return out
+
+
+def _fusion_matches(gmap_vpids, last_cand_vpids, G, Kc):
+    """(2,B,G,Kc) host matrix: [0] every (node j == candidate k) match, [1] only the last candidate per viewpoint."""
     B = len(gmap_vpids)
-    E2 = torch.zeros(2, B, G, Kc, dtype=torch.float32)   # [0]: every match, [1]: last candidate per viewpoint
+    E2 = torch.zeros(2, B, G, Kc, dtype=torch.float32)
     for i in range(B):
         pos = {vp: j for j, vp in enumerate(gmap_vpids[i]) if j > 0}
         last = {}
@@ -94,7 +132,19 @@ def build_sap_fusion(gmap_vpids, gmap_visited_masks, last_cand_vpids, G, Kc, dev
                 last[vp] = (j, k + 1)                     # `tmp[cand_vpid] = ...` overwrites: the last view wins
         for j, k in last.values():
             E2[1, i, j, k] = 1.0
-    if device.type == "cuda":
+    return E2
+
+
+def build_sap_fusion(gmap_vpids, gmap_visited_masks, last_cand_vpids, G, Kc, device):
+    """(B, G, Kc) 0/1 fp32 matrix F with fused[b,j] = global[b,j] + sum_k F[b,j,k] * local[b,k]
+    (pretrain_cmt.py:339-356): slot 0 takes local[0]; an unvisited node takes the local logit of the
+    candidate view that reaches it, otherwise the sum over candidates that lead back to visited nodes.
+    The viewpoint-id matching E[b,j,k] = (node j is candidate k) is host string work; whether a node is
+    visited comes from the device mask, so F is finished on the device without a host synchronisation."""
+    B = len(gmap_vpids)
+    pre = getattr(gmap_vpids, "host_fusion", None)
+    E2 = pre[1] if (pre is not None and pre[0] == (G, Kc)) else _fusion_matches(gmap_vpids, last_cand_vpids, G, Kc)
+    if device.type == "cuda" and not E2.is_pinned():
         E2 = E2.pin_memory()
     E2 = E2.to(device, non_blocking=True)
     vis = gmap_visited_masks.to(torch.float32)                     # (B,G)

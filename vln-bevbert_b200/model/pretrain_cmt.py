@@ -213,9 +213,9 @@ class GlocalTextPathCMTPreTraining(PreTrainedBase):
         Fm = build_sap_fusion(gmap_vpids, gmap_visited_masks, [c[-1] for c in traj_cand_vpids], G, Kc, dev)
         local_fin = local_logits.masked_fill(cand_masks.logical_not(), 0.0)
         fused_logits = global_logits + torch.einsum("bgk,bk->bg", Fm, local_fin)
-        stop_inf = torch.isinf(local_logits[:, 0])
-        if stop_inf.any():  # keep -inf + (-inf) semantics of `fused[:, 0] += local[:, 0]`
-            fused_logits[:, 0] = torch.where(stop_inf, local_logits[:, 0], fused_logits[:, 0])
+        # keep the -inf semantics of `fused[:, 0] += local[:, 0]` (no host sync: unconditional select)
+        fused_logits = torch.cat([torch.where(torch.isinf(local_logits[:, :1]), local_logits[:, :1], fused_logits[:, :1]),
+                                  fused_logits[:, 1:]], 1)
         if not compute_loss:
             return global_logits, local_logits, fused_logits, global_act_labels, local_act_labels
         return F.cross_entropy(global_logits, global_act_labels, reduction="none") + \

@@ -10,7 +10,7 @@ import torch
 from torch import nn
 
 from .. import blocks as Bk
-from .ops import build_gmap_segments, gen_seq_masks, inf_key_mask, neg_key_mask
+from .ops import build_gmap_segments, finish_gmap_segments, gen_seq_masks, inf_key_mask, neg_key_mask
 
 BertLayerNorm = nn.LayerNorm
 
@@ -343,8 +343,12 @@ class GlobalMapEncoder(nn.Module):  # :617-700
                              gmap_vpids, gmap_step_ids, gmap_pos_fts, gmap_lens):
         B, G = gmap_step_ids.shape
         nP, Vtot, Hd = traj_embeds.shape
-        seg = build_gmap_segments(traj_step_lens, traj_vp_lens, traj_vpids, traj_cand_vpids, gmap_vpids, G,
-                                  Vtot, traj_embeds.device)
+        pre = getattr(gmap_vpids, "host_segments", None)      # PreparedList from prepare_batch(): host work already done
+        if pre is not None and pre[0] == (G, Vtot):
+            seg = finish_gmap_segments(pre[1], traj_vp_lens, Vtot, traj_embeds.device)
+        else:
+            seg = build_gmap_segments(traj_step_lens, traj_vp_lens, traj_vpids, traj_cand_vpids, gmap_vpids, G,
+                                      Vtot, traj_embeds.device)
         agg = Bk.run_block(Bk.SegmentSumImpl(), [traj_embeds.reshape(-1, Hd), *seg], []).view(B, G, Hd)
         pos = Bk.run_block(Bk.LinearLNImpl(rt, 1e-12), [gmap_pos_fts],
                            _wb(self.gmap_pos_embeddings[0]) + _wb(self.gmap_pos_embeddings[1]))
