@@ -171,13 +171,21 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"        # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     cfg = full_config()
     model = synth.det_init_(GlocalTextPathCMTPreTraining(cfg), seed=3).to(dev).train()
     net = model
+    reduce_grads = None
     if world > 1:
-        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank], find_unused_parameters=True,
-                                                        gradient_as_bucket_view=True)
+        if args.ddp:        # the reference's wrapping (utils/misc.py:70); heavier on the host
+            net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank], find_unused_parameters=True,
+                                                            gradient_as_bucket_view=True)
+        else:               # one flat NCCL all-reduce of the gradients per step (bevbert_b200/parallel.py)
+            from bevbert_b200.parallel import FlatGradAllReduce, broadcast_parameters
+            broadcast_parameters(model)
+            reduce_grads = FlatGradAllReduce(model.parameters(), world)
     opt = torch.optim.AdamW(model.parameters(), lr=5e-5, weight_decay=0.01, fused=True)
     Bs = args.batch
     scfg = synth.SynthConfig(batch_size=Bs)
@@ -190,6 +198,8 @@ def run_ours(args, rank, world, local_rank):
     def train_step(batch, task):
         loss = net(batch, task).mean()
         loss.backward()
+        if reduce_grads is not None:
+            reduce_grads()
         opt.step()
         opt.zero_grad(set_to_none=True)
         return loss
@@ -225,33 +235,42 @@ def run_ours(args, rank, world, local_rank):
     value = Bs * world * args.steps / (ms * 1e-3)
 
     # ------------------------------------------------------------------ end to end: pinned host -> device each step
+    # Static device input buffers (one set per resident batch), filled from pinned host memory on a copy stream one
+    # step ahead -- the reference's PrefetchLoader (data/loader.py:90-125) without per-step allocations.
     copy_stream = torch.cuda.Stream()
+    dev_in = {(t, j): {k: (torch.empty(v.shape, dtype=v.dtype, device=dev) if torch.is_tensor(v) else v) for k, v in host[t][j].items()}
+              for t in host for j in range(2)}
+    last_use = {}
 
     def fetch(i):
-        t = MIX[i % len(MIX)]
+        t, j = MIX[i % len(MIX)], i % 2
         with torch.cuda.stream(copy_stream):
-            b = synth.batch_to(host[t][i % 2], dev, non_blocking=True)
+            if (t, j) in last_use:
+                copy_stream.wait_event(last_use[(t, j)])      # previous consumer of this buffer set has finished
+            for k, v in host[t][j].items():
+                if torch.is_tensor(v):
+                    dev_in[(t, j)][k].copy_(v, non_blocking=True)
         ev = torch.cuda.Event()
         ev.record(copy_stream)
-        return b, t, ev
+        return dev_in[(t, j)], t, ev, (t, j)
     h2d = sum(tensor_bytes(host[MIX[i % len(MIX)]][i % 2]) for i in range(args.steps)) / args.steps
     sync_all()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
-    nxt = fetch(0)                                   # prefetch like the reference's PrefetchLoader (data/loader.py:90-125)
+    nxt = fetch(0)
     losses, prev = [], None
     for i in range(args.steps):
-        b, t, ev = nxt
+        b, t, ev, key = nxt
         torch.cuda.current_stream().wait_event(ev)
         if i + 1 < args.steps:
             nxt = fetch(i + 1)
         loss = train_step(b, t)
+        done = torch.cuda.Event()
+        done.record()
+        last_use[key] = done
         if prev is not None:
             losses.append(prev.item())               # device -> host read of every step's loss, one step late
         prev = loss.detach()                         # (so the host keeps enqueueing while the GPU finishes the step)
-        for v in b.values():
-            if torch.is_tensor(v):
-                v.record_stream(torch.cuda.current_stream())
     losses.append(prev.item())
     e3.record()
     sync_all()
@@ -353,6 +372,7 @@ def main():
     ap.add_argument("--batch", type=int, default=32, help="samples per GPU per step")
     ap.add_argument("--ref-batch", type=int, default=2, help="batch of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ddp", action="store_true", help="wrap with torch DDP instead of the flat gradient all-reduce")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))

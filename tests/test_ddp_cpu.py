@@ -1,6 +1,6 @@
 """N > 1 path on CPU (gloo, world_size 2): the model under torch DistributedDataParallel
-(find_unused_parameters=True, as pretrain_src/utils/misc.py:70) gives, after the gradient all-reduce, the
-gradients of a single process on the concatenated batch.  Kernels are emulated (tests/emu_kernels.py)."""
+(find_unused_parameters=True, as pretrain_src/utils/misc.py:70), and under the flat gradient all-reduce of
+bevbert_b200/parallel.py, gives the gradients of a single process on the concatenated batch.  Kernels are emulated (tests/emu_kernels.py)."""
 import os
 import socket
 import sys
@@ -13,7 +13,7 @@ import torch.multiprocessing as mp
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-def _worker(rank, world, port, task, ret):
+def _worker(rank, world, port, task, ret, mode="ddp"):
     sys.path.insert(0, os.path.dirname(HERE))
     sys.path.insert(0, HERE)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
@@ -28,8 +28,14 @@ def _worker(rank, world, port, task, ret):
     full = synth.make_batch(small_synth(batch_size=4), seed=9, task=task)
     shard = synth.split_batch(full, world)[rank]
     model = synth.det_init_(GlocalTextPathCMTPreTraining(cfg), seed=3).train()
-    ddp = torch.nn.parallel.DistributedDataParallel(model, find_unused_parameters=True)
-    ddp(shard, task).mean().backward()
+    if mode == "ddp":
+        ddp = torch.nn.parallel.DistributedDataParallel(model, find_unused_parameters=True)
+        ddp(shard, task).mean().backward()
+    else:       # bevbert_b200.parallel: one flat all-reduce after backward (what bench.py runs at N > 1)
+        from bevbert_b200.parallel import FlatGradAllReduce, broadcast_parameters
+        broadcast_parameters(model)
+        model(shard, task).mean().backward()
+        FlatGradAllReduce(model.parameters(), world)()
     grads = {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None}
     if rank == 0:
         single = synth.det_init_(GlocalTextPathCMTPreTraining(cfg), seed=3).train()
@@ -45,13 +51,14 @@ def _worker(rank, world, port, task, ret):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("task", ["sap", "mlm"])
-def test_ddp_gradients_equal_single_process(task):
+@pytest.mark.parametrize("task,mode", [("sap", "ddp"), ("mlm", "ddp"), ("sap", "flat"), ("mlm", "flat")])
+# (masksem averages over a per-shard count of masked cells, so mean-of-shard-means != global mean in the reference too)
+def test_ddp_gradients_equal_single_process(task, mode):
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]
     s.close()
     mgr = mp.Manager()
     ret = mgr.dict()
-    mp.spawn(_worker, args=(2, port, task, ret), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, port, task, ret, mode), nprocs=2, join=True)
     assert ret["worst"] < 1e-3, ret["worst"]

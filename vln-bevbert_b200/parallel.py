@@ -1,0 +1,46 @@
+"""Data-parallel gradient exchange for the hot path: one NCCL all-reduce over NVLink per step on a flat fp32
+bucket of the gradients.
+
+The model also runs unchanged under `torch.nn.parallel.DistributedDataParallel(find_unused_parameters=True)`
+(what `pretrain_src/utils/misc.py:64-77` does; tests/test_ddp_cpu.py).  This helper is the lighter path used by
+bench.py: DDP's per-parameter hooks and per-step unused-parameter graph search cost several milliseconds of host
+time per step on a path that is already launch-bound, while every rank runs the same task in a step
+(`data/loader.py:50-61` broadcasts the task id), so the set of parameters that received a gradient is identical
+on all ranks and one coalesced all-reduce suffices.
+"""
+import torch
+import torch.distributed as dist
+
+
+class FlatGradAllReduce:
+    """all-reduce (average) the gradients of `params` through one flat buffer per step."""
+
+    def __init__(self, params, world_size=None):
+        self.params = [p for p in params if p.requires_grad]
+        self.world = world_size or (dist.get_world_size() if dist.is_initialized() else 1)
+        self.buf = None
+
+    @torch.no_grad()
+    def __call__(self):
+        if self.world == 1:
+            return
+        grads = [p.grad for p in self.params if p.grad is not None]
+        if not grads:
+            return
+        n = sum(g.numel() for g in grads)
+        if self.buf is None or self.buf.numel() < n:
+            self.buf = torch.empty(n, dtype=torch.float32, device=grads[0].device)
+        flat = self.buf[:n]
+        views = list(torch.split(flat, [g.numel() for g in grads]))
+        torch._foreach_copy_(views, [g.reshape(-1) for g in grads])
+        flat.mul_(1.0 / self.world)
+        dist.all_reduce(flat)
+        torch._foreach_copy_([g.view(-1) if g.is_contiguous() else g.reshape(-1) for g in grads], views)
+
+
+def broadcast_parameters(model, src=0):
+    """rank `src` -> all, once (the DDP constructor's initial broadcast, utils/misc.py:71-72)."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return
+    for t in list(model.parameters()) + list(model.buffers()):
+        dist.broadcast(t.data, src)
