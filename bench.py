@@ -308,9 +308,10 @@ def run_ours(args, rank, world, local_rank):
         top = sorted(by_shape.items(), key=lambda kv: -kv[1][1])[:14]
         shape_rows = [{"MNKb_amn_bmn": list(k), "launches": v[0], "ms": round(v[1], 3),
                        "tflops": round(v[2] / (v[1] * 1e-3) / 1e12, 1)} for k, v in top]
-        if os.environ.get("BEVBERT_BENCH_VERBOSE"):
-            for r in shape_rows:
-                print("gemm-shape", r, file=sys.stderr)
+        if os.environ.get("BEVBERT_BENCH_VERBOSE"):      # every shape, to stderr (for profiles/)
+            for k, v in sorted(by_shape.items(), key=lambda kv: -kv[1][1]):
+                print("gemm-shape M,N,K,batch,a_mn,b_mn=%s launches=%d ms=%.3f tflops=%.1f" % (
+                    list(k), v[0], v[1], v[2] / (v[1] * 1e-3) / 1e12), file=sys.stderr)
         roof = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05, all %d launches of one 11-step mix cycle)" % len(rec),
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "peak_source": "%s bf16_tflops_sustained (kernel timed inside a long step)" % peaks["source"],

@@ -58,3 +58,21 @@ def test_prepare_batch_gives_identical_results(emu):
         a = model(synth.clone_batch(b), task)
         c = model(prepare_batch(synth.clone_batch(b)), task)
         assert torch.equal(a, c)
+
+
+def test_step_arena_gives_identical_gradients(emu):
+    """The per-step zero arena (blocks.ARENA: one fill per step for all accumulate-into gradient buffers) is used from
+    the second step of a task on and changes no gradient; gradients of an earlier step stay valid after the next."""
+    from bevbert_b200 import blocks
+    cfg, scfg = small_config(), small_synth()
+    model = synth.det_init_(GlocalTextPathCMTPreTraining(cfg), seed=3).train()
+    b = synth.make_batch(scfg, seed=13, task="sap")
+    grads = []
+    for step in range(3):
+        model.zero_grad(set_to_none=True)
+        model(synth.clone_batch(b), "sap").mean().backward()
+        if step:
+            assert blocks.ARENA.buf is not None and blocks.ARENA.off > 0
+        grads.append({n: p.grad for n, p in model.named_parameters() if p.grad is not None})
+    for n, g in grads[0].items():
+        assert torch.equal(g, grads[1][n]) and torch.equal(g, grads[2][n]), n

@@ -79,6 +79,8 @@ attn_scores_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();
+  pdl_trigger();
   const int ncols = (p.nk + 15) & ~15;  // columns the MMAs produce
 
   if (warp == 0) {
@@ -379,7 +381,7 @@ extern "C" int bb_attn_scores(const bb_attn_scores_args* a, void* stream_) {
   const long long total = (long long)p.m_tiles * a->H * a->B;
   const int grid = total < num_sms ? (int)total : num_sms;
   const size_t smem_bytes = (size_t)AS_STAGES * AS_STAGE + 1024 + 256 + (2 * 512 + 8 * 128) * sizeof(float);
-  attn_scores_kernel<<<grid, AS_THREADS, smem_bytes, stream>>>(ta, tb, p, (int)total);
+  bb::launch_pdl(attn_scores_kernel, grid, AS_THREADS, smem_bytes, stream, ta, tb, p, (int)total);
   count_launch();
   return check_launch("attn_scores_kernel");
 }

@@ -11,6 +11,7 @@
 
 #include "../../include/bevbert_b200.h"
 #include "common.h"
+#include "ptx.cuh"
 
 namespace bb {
 
@@ -22,6 +23,8 @@ __global__ void lift_index_kernel(const float* __restrict__ depths, const float*
                                   const float* __restrict__ S_w2c, const float* __restrict__ T_w2c, int B, int V, int Hf,
                                   int Wf, float depth_scale, float fx, float fy, float cx, float cy, int D, float res,
                                   float half, float y_clip, int32_t* __restrict__ cell_idx, float* __restrict__ pc_out) {
+  bb::pdl_wait();
+  bb::pdl_trigger();
   const int P = V * Hf * Wf;
   const long long gid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (gid >= (long long)B * P) return;
@@ -89,6 +92,8 @@ __global__ void __launch_bounds__(SC_WARPS * 32)
 scatter_mean_f32_kernel(const float* __restrict__ feats, const int32_t* __restrict__ cell_idx, int P, int C, int ncell,
                         float* __restrict__ bev_f32, __nv_bfloat16* __restrict__ bev_bf16,
                         uint8_t* __restrict__ ob_mask, int32_t* __restrict__ counts) {
+  bb::pdl_wait();
+  bb::pdl_trigger();
   extern __shared__ int32_t sidx[];
   const int b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -168,6 +173,8 @@ scatter_mean_f32_kernel(const float* __restrict__ feats, const int32_t* __restri
 __global__ void __launch_bounds__(SC_WARPS * 32)
 scatter_sem_f64_kernel(const double* __restrict__ sems, const int32_t* __restrict__ cell_idx, int P, int S, int ncell,
                        double* __restrict__ bev_sem, uint8_t* __restrict__ sem_mask) {
+  bb::pdl_wait();
+  bb::pdl_trigger();
   extern __shared__ int32_t sidx[];
   const int b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -215,7 +222,7 @@ extern "C" int bb_bev_lift_index(const float* depths, const float* T_c2w, const 
   if (B <= 0) return 0;
   const long long n = (long long)B * V * Hf * Wf;
   const float half = (float)((map_dim - 1) / 2.0);  // (map_dim-1)/2 as in bev_utils.py:393
-  lift_index_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+  bb::launch_pdl(lift_index_kernel, (unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream, 
       depths, T_c2w, S_w2c, T_w2c, B, V, Hf, Wf, depth_scale, fx, fy, cx, cy, map_dim, map_res, half, y_clip, cell_idx,
       pc_out);
   count_launch();
@@ -237,7 +244,7 @@ extern "C" int bb_bev_scatter_mean_f32(const float* feats, const int32_t* cell_i
     attr_set = true;
   }
   dim3 grid((ncell + SC_WARPS - 1) / SC_WARPS, B);
-  scatter_mean_f32_kernel<<<grid, SC_WARPS * 32, (size_t)P * 4, (cudaStream_t)stream>>>(
+  bb::launch_pdl(scatter_mean_f32_kernel, grid, SC_WARPS * 32, (size_t)P * 4, (cudaStream_t)stream, 
       feats, cell_idx, P, C, ncell, bev_f32, reinterpret_cast<__nv_bfloat16*>(bev_bf16), ob_mask, counts);
   count_launch();
   return check_launch("scatter_mean_f32_kernel");
@@ -256,7 +263,7 @@ extern "C" int bb_bev_scatter_sem_f64(const double* sems, const int32_t* cell_id
     attr_set = true;
   }
   dim3 grid((ncell + SC_WARPS - 1) / SC_WARPS, B);
-  scatter_sem_f64_kernel<<<grid, SC_WARPS * 32, (size_t)P * 4, (cudaStream_t)stream>>>(sems, cell_idx, P, S, ncell,
+  bb::launch_pdl(scatter_sem_f64_kernel, grid, SC_WARPS * 32, (size_t)P * 4, (cudaStream_t)stream, sems, cell_idx, P, S, ncell,
                                                                                     bev_sem, sem_mask);
   count_launch();
   return check_launch("scatter_sem_f64_kernel");

@@ -1,5 +1,6 @@
 // Error reporting and launch accounting for the C ABI (include/bevbert_b200.h).
 #include <atomic>
+#include <stdlib.h>
 #include <stdio.h>
 #include <string.h>
 
@@ -23,6 +24,13 @@ int check_launch(const char* what) {
   return set_error(buf);
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("BB_PDL");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
 }  // namespace bb
 
 extern "C" const char* bb_last_error(void) { return bb::g_err; }

@@ -7,4 +7,24 @@ namespace bb {
 int set_error(const char* msg);          // stores msg, returns -1
 int check_launch(const char* what);      // cudaGetLastError -> 0 / -1 (+message)
 void count_launch(int n = 1);
+bool pdl_enabled();                      // BB_PDL env (default on)
+
+// Launch with programmatic dependent launch allowed: the kernel may become resident while the previous kernel on
+// the stream drains; every kernel launched this way executes griddepcontrol.wait (bb::pdl_wait) before it touches
+// global memory, so ordering is unchanged and only launch latency / prologue overlap the predecessor's tail.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 }  // namespace bb

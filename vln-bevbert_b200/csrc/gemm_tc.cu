@@ -115,6 +115,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  // Everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the previous kernel's tail;
+  // from here on global memory is read and written.
+  pdl_wait();
+  pdl_trigger();
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -562,7 +566,7 @@ extern "C" int bb_gemm_bf16(const bb_gemm_args* a, void* stream_) {
     rec->dims[4] = p.a_mn; rec->dims[5] = p.b_mn;
     cudaEventRecord(rec->e0, stream);
   }
-  gemm_tc_kernel<<<grid, NUM_THREADS, smem_bytes, stream>>>(ta, tb, p, (int)total);
+  bb::launch_pdl(gemm_tc_kernel, grid, NUM_THREADS, smem_bytes, stream, ta, tb, p, (int)total);
   if (rec) cudaEventRecord(rec->e1, stream);
   count_launch();
   return check_launch("gemm_tc_kernel");

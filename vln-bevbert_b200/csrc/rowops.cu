@@ -55,6 +55,8 @@ __device__ __forceinline__ void store8(float* p, const float (&v)[8]) {
 // ------------------------------------------------------------------------------------- casts
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, long long n, uint64_t seed,
                                      uint32_t thresh, float scale) {
+  bb::pdl_wait();
+  bb::pdl_trigger();
   const long long stride = (long long)gridDim.x * blockDim.x * 8;
   for (long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 8; i < n; i += stride) {
     if (i + 8 <= n) {
@@ -75,6 +77,8 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, bf16* __rest
   }
 }
 __global__ void cast_bf16_f32_kernel(const bf16* __restrict__ src, float* __restrict__ dst, long long n) {
+  bb::pdl_wait();
+  bb::pdl_trigger();
   const long long stride = (long long)gridDim.x * blockDim.x * 8;
   for (long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 8; i < n; i += stride) {
     if (i + 8 <= n) {
@@ -88,6 +92,8 @@ __global__ void cast_bf16_f32_kernel(const bf16* __restrict__ src, float* __rest
 }
 __global__ void add_bf16_kernel(const bf16* __restrict__ a, const bf16* __restrict__ b, bf16* __restrict__ out,
                                 long long n) {
+  bb::pdl_wait();
+  bb::pdl_trigger();
   const long long stride = (long long)gridDim.x * blockDim.x * 8;
   for (long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 8; i < n; i += stride) {
     if (i + 8 <= n) {
@@ -104,6 +110,8 @@ __global__ void add_bf16_kernel(const bf16* __restrict__ a, const bf16* __restri
 }
 __global__ void dropout_bf16_kernel(const bf16* __restrict__ src, bf16* __restrict__ dst, long long n, uint64_t seed,
                                     uint32_t thresh, float scale) {
+  bb::pdl_wait();
+  bb::pdl_trigger();
   const long long stride = (long long)gridDim.x * blockDim.x * 8;
   for (long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 8; i < n; i += stride) {
     if (i + 8 <= n) {
@@ -120,6 +128,8 @@ __global__ void dropout_bf16_kernel(const bf16* __restrict__ src, bf16* __restri
 }
 __global__ void act_bwd_bf16_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ aux, int mode,
                                     bf16* __restrict__ out, long long n) {
+  bb::pdl_wait();
+  bb::pdl_trigger();
   const long long stride = (long long)gridDim.x * blockDim.x * 8;
   for (long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 8; i < n; i += stride) {
     if (i + 8 <= n) {
@@ -141,6 +151,8 @@ __global__ void act_bwd_bf16_kernel(const bf16* __restrict__ dy, const bf16* __r
 __global__ void add_rows_kernel(const bf16* __restrict__ a, const bf16* __restrict__ b, const float* __restrict__ table,
                                 const int64_t* __restrict__ idx, const float* __restrict__ vec, long long rows, int H,
                                 bf16* __restrict__ out) {
+  bb::pdl_wait();
+  bb::pdl_trigger();
   const int h8 = H / 8;
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= rows * h8) return;
@@ -169,6 +181,8 @@ __global__ void add_rows_kernel(const bf16* __restrict__ a, const bf16* __restri
   store8(out + r * H + c, v);
 }
 __global__ void scale_rows_bf16_kernel(bf16* __restrict__ x, const float* __restrict__ g, long long rows, long long ld) {
+  bb::pdl_wait();
+  bb::pdl_trigger();
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= rows * ld) return;
   x[i] = __float2bfloat16(__bfloat162float(x[i]) * g[i / ld]);
@@ -177,6 +191,8 @@ __global__ void scale_rows_bf16_kernel(bf16* __restrict__ x, const float* __rest
 __global__ void segment_wsum_kernel(const bf16* __restrict__ src, const int32_t* __restrict__ seg_off,
                                     const int32_t* __restrict__ idx, const float* __restrict__ w, long long nseg, int H,
                                     bf16* __restrict__ out) {
+  bb::pdl_wait();
+  bb::pdl_trigger();
   const int lane = threadIdx.x & 31;
   const long long s = blockIdx.x * 8LL + (threadIdx.x >> 5);
   if (s >= nseg) return;
@@ -198,6 +214,8 @@ __global__ void segment_wsum_kernel(const bf16* __restrict__ src, const int32_t*
 __global__ void segment_wsum_bwd_kernel(const bf16* __restrict__ dout, const int32_t* __restrict__ seg_off,
                                         const int32_t* __restrict__ idx, const float* __restrict__ w, long long nseg,
                                         int H, float* __restrict__ dsrc) {
+  bb::pdl_wait();
+  bb::pdl_trigger();
   const int lane = threadIdx.x & 31;
   const long long s = blockIdx.x * 8LL + (threadIdx.x >> 5);
   if (s >= nseg) return;
@@ -214,6 +232,8 @@ __global__ void segment_wsum_bwd_kernel(const bf16* __restrict__ dout, const int
   }
 }
 __global__ void axpy_f32_from_bf16_kernel(const bf16* __restrict__ x, float* __restrict__ y, long long n) {
+  bb::pdl_wait();
+  bb::pdl_trigger();
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += stride)
     y[i] += __bfloat162float(x[i]);
@@ -230,6 +250,8 @@ layernorm_fwd_kernel(const XT* __restrict__ x, const bf16* __restrict__ res, con
                      uint32_t thresh_in, float scale_in, uint64_t seed_out, uint32_t thresh_out, float scale_out,
                      bf16* __restrict__ y, float* __restrict__ y_f32, float* __restrict__ mean_out,
                      float* __restrict__ rstd_out) {
+  bb::pdl_wait();
+  bb::pdl_trigger();
   const int lane = threadIdx.x & 31;
   const long long row = blockIdx.x * (long long)LN_WARPS + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -302,6 +324,8 @@ layernorm_bwd_kernel(const DYT* __restrict__ dy, const XT* __restrict__ x, const
                      float scale_in, uint64_t seed_out, uint32_t thresh_out, float scale_out, DXT* __restrict__ dx,
                      bf16* __restrict__ dres, float* __restrict__ dgamma, float* __restrict__ dbeta,
                      float* __restrict__ dxsum) {
+  bb::pdl_wait();
+  bb::pdl_trigger();
   extern __shared__ float ln_part[];  // [2][LN_WARPS][H] per-warp partial dgamma / dbeta (no atomics, no conflicts)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float pg[LN_MAXCH][8], pb[LN_MAXCH][8], px[LN_MAXCH][8];
@@ -399,6 +423,8 @@ layernorm_bwd_kernel(const DYT* __restrict__ dy, const XT* __restrict__ x, const
 // ------------------------------------------------------------------------------------- column sums
 __global__ void __launch_bounds__(256)
 colsum_bf16_kernel(const bf16* __restrict__ x, long long rows, int N, long long ld, float* __restrict__ out) {
+  bb::pdl_wait();
+  bb::pdl_trigger();
   // blockDim = (32, 8): 32 lanes x 8 columns each = 256 columns per block in x; rows strided over y and grid.y
   __shared__ float part[8][256];
   const int col = blockIdx.x * 256 + threadIdx.x * 8;
@@ -436,6 +462,8 @@ __global__ void __launch_bounds__(256)
 softmax_fwd_kernel(const float* __restrict__ scores, const float* __restrict__ kmask, const float* __restrict__ bias,
                    long long nrows, int H, int nq, int nk, int ld, uint64_t seed, uint32_t thresh, float scale,
                    bf16* __restrict__ probs, bf16* __restrict__ probs_drop) {
+  bb::pdl_wait();
+  bb::pdl_trigger();
   const int lane = threadIdx.x & 31;
   const long long row = blockIdx.x * 8LL + (threadIdx.x >> 5);
   if (row >= nrows) return;
@@ -491,6 +519,8 @@ __global__ void __launch_bounds__(256)
 softmax_bwd_kernel(const bf16* __restrict__ probs, const float* __restrict__ dprobs, long long nrows, int H, int nq,
                    int nk, int ld, uint64_t seed, uint32_t thresh, float scale, float out_scale, bf16* __restrict__ ds,
                    float* __restrict__ dbias) {
+  bb::pdl_wait();
+  bb::pdl_trigger();
   const int lane = threadIdx.x & 31;
   const long long row = blockIdx.x * 8LL + (threadIdx.x >> 5);
   if (row >= nrows) return;
@@ -531,6 +561,8 @@ softmax_bwd_kernel(const bf16* __restrict__ probs, const float* __restrict__ dpr
 __global__ void embed_sum_kernel(const int64_t* __restrict__ ids, const float* __restrict__ word,
                                  const float* __restrict__ pos, const float* __restrict__ type0, long long ntok, int L,
                                  int H, float* __restrict__ out) {
+  bb::pdl_wait();
+  bb::pdl_trigger();
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;  // over ntok * H/4
   const int h4 = H / 4;
   if (i >= ntok * h4) return;
@@ -550,6 +582,8 @@ __global__ void embed_sum_kernel(const int64_t* __restrict__ ids, const float* _
 __global__ void embed_scatter_grad_kernel(const int64_t* __restrict__ ids, const float* __restrict__ dz, long long ntok,
                                           int L, int H, int64_t padding_idx, float* __restrict__ dword,
                                           float* __restrict__ dpos, float* __restrict__ dtype0) {
+  bb::pdl_wait();
+  bb::pdl_trigger();
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= ntok * H) return;
   const long long tok = i / H;
@@ -565,6 +599,8 @@ __global__ void embed_scatter_grad_kernel(const int64_t* __restrict__ ids, const
 // ------------------------------------------------------------------------------------- gather / scatter rows
 __global__ void gather_rows_bf16_kernel(const bf16* __restrict__ in, const int64_t* __restrict__ idx, long long nout,
                                         int H, bf16* __restrict__ out) {
+  bb::pdl_wait();
+  bb::pdl_trigger();
   const int h8 = H / 8;
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= nout * h8) return;
@@ -577,6 +613,8 @@ __global__ void gather_rows_bf16_kernel(const bf16* __restrict__ in, const int64
 }
 __global__ void scatter_add_rows_kernel(const bf16* __restrict__ in, const int64_t* __restrict__ idx, long long nin,
                                         int H, float* __restrict__ out) {
+  bb::pdl_wait();
+  bb::pdl_trigger();
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= nin * H) return;
   const long long r = i / H;
@@ -589,6 +627,8 @@ __global__ void scatter_add_rows_kernel(const bf16* __restrict__ in, const int64
 __global__ void __launch_bounds__(256)
 softmax_xent_kernel(const float* __restrict__ logits, const int64_t* __restrict__ labels, int V, long long ld,
                     float* __restrict__ loss, const float* __restrict__ gscale, bf16* __restrict__ dlogits) {
+  bb::pdl_wait();
+  bb::pdl_trigger();
   __shared__ float red[8];
   __shared__ float bcast;
   const long long row = blockIdx.x;
@@ -650,14 +690,14 @@ extern "C" int bb_cast_f32_bf16(const float* src, void* dst, int64_t n, uint64_t
                                 void* stream) {
   if (n <= 0) return 0;
   if (((uintptr_t)src & 15) || ((uintptr_t)dst & 15)) return set_error("bb_cast_f32_bf16: pointers must be 16B aligned");
-  cast_f32_bf16_kernel<<<grid1d(n, 256 * 8), 256, 0, STREAM>>>(src, (bf16*)dst, n, seed, thresh, scale);
+  bb::launch_pdl(cast_f32_bf16_kernel, grid1d(n, 256 * 8), 256, 0, STREAM, src, (bf16*)dst, n, seed, thresh, scale);
   count_launch();
   return check_launch("cast_f32_bf16_kernel");
 }
 extern "C" int bb_cast_bf16_f32(const void* src, float* dst, int64_t n, void* stream) {
   if (n <= 0) return 0;
   if (((uintptr_t)src & 15) || ((uintptr_t)dst & 15)) return set_error("bb_cast_bf16_f32: pointers must be 16B aligned");
-  cast_bf16_f32_kernel<<<grid1d(n, 256 * 8), 256, 0, STREAM>>>((const bf16*)src, dst, n);
+  bb::launch_pdl(cast_bf16_f32_kernel, grid1d(n, 256 * 8), 256, 0, STREAM, (const bf16*)src, dst, n);
   count_launch();
   return check_launch("cast_bf16_f32_kernel");
 }
@@ -665,7 +705,7 @@ extern "C" int bb_add_bf16(const void* a, const void* b, void* out, int64_t n, v
   if (n <= 0) return 0;
   if (((uintptr_t)a & 15) || ((uintptr_t)b & 15) || ((uintptr_t)out & 15))
     return set_error("bb_add_bf16: pointers must be 16B aligned");
-  add_bf16_kernel<<<grid1d(n, 256 * 8), 256, 0, STREAM>>>((const bf16*)a, (const bf16*)b, (bf16*)out, n);
+  bb::launch_pdl(add_bf16_kernel, grid1d(n, 256 * 8), 256, 0, STREAM, (const bf16*)a, (const bf16*)b, (bf16*)out, n);
   count_launch();
   return check_launch("add_bf16_kernel");
 }
@@ -673,7 +713,7 @@ extern "C" int bb_dropout_bf16(const void* src, void* dst, int64_t n, uint64_t s
                                void* stream) {
   if (n <= 0) return 0;
   if (((uintptr_t)src & 15) || ((uintptr_t)dst & 15)) return set_error("bb_dropout_bf16: pointers must be 16B aligned");
-  dropout_bf16_kernel<<<grid1d(n, 256 * 8), 256, 0, STREAM>>>((const bf16*)src, (bf16*)dst, n, seed, thresh, scale);
+  bb::launch_pdl(dropout_bf16_kernel, grid1d(n, 256 * 8), 256, 0, STREAM, (const bf16*)src, (bf16*)dst, n, seed, thresh, scale);
   count_launch();
   return check_launch("dropout_bf16_kernel");
 }
@@ -682,7 +722,7 @@ extern "C" int bb_act_bwd_bf16(const void* dy, const void* aux, int mode, void* 
   if (mode != 1 && mode != 2) return set_error("bb_act_bwd_bf16: mode must be 1 (gelu) or 2 (relu)");
   if (((uintptr_t)dy & 15) || ((uintptr_t)aux & 15) || ((uintptr_t)out & 15))
     return set_error("bb_act_bwd_bf16: pointers must be 16B aligned");
-  act_bwd_bf16_kernel<<<grid1d(n, 256 * 8), 256, 0, STREAM>>>((const bf16*)dy, (const bf16*)aux, mode, (bf16*)out, n);
+  bb::launch_pdl(act_bwd_bf16_kernel, grid1d(n, 256 * 8), 256, 0, STREAM, (const bf16*)dy, (const bf16*)aux, mode, (bf16*)out, n);
   count_launch();
   return check_launch("act_bwd_bf16_kernel");
 }
@@ -692,7 +732,7 @@ extern "C" int bb_add_rows(const void* a, const void* b, const float* table, con
   if (H % 8 != 0) return set_error("bb_add_rows: H must be a multiple of 8");
   if (table && !idx) return set_error("bb_add_rows: table needs idx");
   const long long n = rows * (H / 8);
-  add_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, STREAM>>>((const bf16*)a, (const bf16*)b, table, idx, vec,
+  bb::launch_pdl(add_rows_kernel, (unsigned)((n + 255) / 256), 256, 0, STREAM, (const bf16*)a, (const bf16*)b, table, idx, vec,
                                                                    rows, H, (bf16*)out);
   count_launch();
   return check_launch("add_rows_kernel");
@@ -700,7 +740,7 @@ extern "C" int bb_add_rows(const void* a, const void* b, const float* table, con
 extern "C" int bb_scale_rows_bf16(void* x, const float* g, int64_t rows, int64_t ld, void* stream) {
   if (rows <= 0) return 0;
   const long long n = rows * ld;
-  scale_rows_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, STREAM>>>((bf16*)x, g, rows, ld);
+  bb::launch_pdl(scale_rows_bf16_kernel, (unsigned)((n + 255) / 256), 256, 0, STREAM, (bf16*)x, g, rows, ld);
   count_launch();
   return check_launch("scale_rows_bf16_kernel");
 }
@@ -708,7 +748,7 @@ extern "C" int bb_segment_wsum(const void* src, const int32_t* seg_off, const in
                                int64_t nseg, int H, void* out, void* stream) {
   if (nseg <= 0) return 0;
   if (H % 8 != 0) return set_error("bb_segment_wsum: H must be a multiple of 8");
-  segment_wsum_kernel<<<(unsigned)((nseg + 7) / 8), 256, 0, STREAM>>>((const bf16*)src, seg_off, idx, w, nseg, H,
+  bb::launch_pdl(segment_wsum_kernel, (unsigned)((nseg + 7) / 8), 256, 0, STREAM, (const bf16*)src, seg_off, idx, w, nseg, H,
                                                                       (bf16*)out);
   count_launch();
   return check_launch("segment_wsum_kernel");
@@ -717,14 +757,14 @@ extern "C" int bb_segment_wsum_bwd(const void* dout, const int32_t* seg_off, con
                                    int64_t nseg, int H, float* dsrc_f32, void* stream) {
   if (nseg <= 0) return 0;
   if (H % 8 != 0) return set_error("bb_segment_wsum_bwd: H must be a multiple of 8");
-  segment_wsum_bwd_kernel<<<(unsigned)((nseg + 7) / 8), 256, 0, STREAM>>>((const bf16*)dout, seg_off, idx, w, nseg, H,
+  bb::launch_pdl(segment_wsum_bwd_kernel, (unsigned)((nseg + 7) / 8), 256, 0, STREAM, (const bf16*)dout, seg_off, idx, w, nseg, H,
                                                                           dsrc_f32);
   count_launch();
   return check_launch("segment_wsum_bwd_kernel");
 }
 extern "C" int bb_axpy_f32_from_bf16(const void* x, float* y, int64_t n, void* stream) {
   if (n <= 0) return 0;
-  axpy_f32_from_bf16_kernel<<<grid1d(n, 256), 256, 0, STREAM>>>((const bf16*)x, y, n);
+  bb::launch_pdl(axpy_f32_from_bf16_kernel, grid1d(n, 256), 256, 0, STREAM, (const bf16*)x, y, n);
   count_launch();
   return check_launch("axpy_f32_from_bf16_kernel");
 }
@@ -737,11 +777,11 @@ extern "C" int bb_layernorm_fwd(const void* x, int x_f32, const void* residual, 
   if (H % 8 != 0 || H > LN_MAXCH * 256) return set_error("bb_layernorm_fwd: H must be a multiple of 8 and <= 1024");
   const unsigned grid = (unsigned)((rows + LN_WARPS - 1) / LN_WARPS);
   if (x_f32)
-    layernorm_fwd_kernel<float><<<grid, LN_WARPS * 32, 0, STREAM>>>(
+    bb::launch_pdl(layernorm_fwd_kernel<float>, grid, LN_WARPS * 32, 0, STREAM, 
         (const float*)x, (const bf16*)residual, gamma, beta, eps, rows, H, seed_in, thresh_in, scale_in, seed_out,
         thresh_out, scale_out, (bf16*)y, y_f32, mean, rstd);
   else
-    layernorm_fwd_kernel<bf16><<<grid, LN_WARPS * 32, 0, STREAM>>>(
+    bb::launch_pdl(layernorm_fwd_kernel<bf16>, grid, LN_WARPS * 32, 0, STREAM, 
         (const bf16*)x, (const bf16*)residual, gamma, beta, eps, rows, H, seed_in, thresh_in, scale_in, seed_out,
         thresh_out, scale_out, (bf16*)y, y_f32, mean, rstd);
   count_launch();
@@ -772,7 +812,7 @@ extern "C" int bb_layernorm_bwd(const void* dy, int dy_f32, const void* x, int x
     }
   }
 #define LN_BWD(DYT, XT, DXT)                                                                                        \
-  layernorm_bwd_kernel<DYT, XT, DXT><<<grid, LN_WARPS * 32, ln_smem, STREAM>>>(                                     \
+  bb::launch_pdl(layernorm_bwd_kernel<DYT, XT, DXT>, grid, LN_WARPS * 32, ln_smem, STREAM,                                      \
       (const DYT*)dy, (const XT*)x, (const bf16*)residual, gamma, mean, rstd, rows, H, seed_in, thresh_in, scale_in, \
       seed_out, thresh_out, scale_out, (DXT*)dx, (bf16*)dres, dgamma, dbeta, dxsum)
   if (!dy_f32 && !x_f32 && !dx_f32) LN_BWD(bf16, bf16, bf16);
@@ -792,7 +832,7 @@ extern "C" int bb_colsum_bf16(const void* x, int64_t rows, int N, int64_t ld, fl
   long long gy = (rows + 63) / 64;
   if (gy > 64) gy = 64;
   dim3 grid((N + 255) / 256, (unsigned)gy);
-  colsum_bf16_kernel<<<grid, dim3(32, 8), 0, STREAM>>>((const bf16*)x, rows, N, ld, out);
+  bb::launch_pdl(colsum_bf16_kernel, grid, dim3(32, 8), 0, STREAM, (const bf16*)x, rows, N, ld, out);
   count_launch();
   return check_launch("colsum_bf16_kernel");
 }
@@ -805,13 +845,13 @@ extern "C" int bb_softmax_fwd(const float* scores, const float* kmask, const flo
   if (ld < nk || ld > 1024) return set_error("bb_softmax_fwd: need nk <= ld <= 1024");
   const unsigned grid = (unsigned)((nrows + 7) / 8);
   if (ld <= 128)
-    softmax_fwd_kernel<4><<<grid, 256, 0, STREAM>>>(scores, kmask, bias, nrows, H, nq, nk, ld, seed, thresh, scale,
+    bb::launch_pdl(softmax_fwd_kernel<4>, grid, 256, 0, STREAM, scores, kmask, bias, nrows, H, nq, nk, ld, seed, thresh, scale,
                                                     (bf16*)probs, (bf16*)probs_drop);
   else if (ld <= 512)
-    softmax_fwd_kernel<16><<<grid, 256, 0, STREAM>>>(scores, kmask, bias, nrows, H, nq, nk, ld, seed, thresh, scale,
+    bb::launch_pdl(softmax_fwd_kernel<16>, grid, 256, 0, STREAM, scores, kmask, bias, nrows, H, nq, nk, ld, seed, thresh, scale,
                                                      (bf16*)probs, (bf16*)probs_drop);
   else
-    softmax_fwd_kernel<32><<<grid, 256, 0, STREAM>>>(scores, kmask, bias, nrows, H, nq, nk, ld, seed, thresh, scale,
+    bb::launch_pdl(softmax_fwd_kernel<32>, grid, 256, 0, STREAM, scores, kmask, bias, nrows, H, nq, nk, ld, seed, thresh, scale,
                                                      (bf16*)probs, (bf16*)probs_drop);
   count_launch();
   return check_launch("softmax_fwd_kernel");
@@ -825,13 +865,13 @@ extern "C" int bb_softmax_bwd(const void* probs, const float* dprobs, int nbatch
   if (ld < nk || ld > 1024) return set_error("bb_softmax_bwd: need nk <= ld <= 1024");
   const unsigned grid = (unsigned)((nrows + 7) / 8);
   if (ld <= 128)
-    softmax_bwd_kernel<4><<<grid, 256, 0, STREAM>>>((const bf16*)probs, dprobs, nrows, H, nq, nk, ld, seed, thresh,
+    bb::launch_pdl(softmax_bwd_kernel<4>, grid, 256, 0, STREAM, (const bf16*)probs, dprobs, nrows, H, nq, nk, ld, seed, thresh,
                                                     scale, out_scale, (bf16*)ds, dbias);
   else if (ld <= 512)
-    softmax_bwd_kernel<16><<<grid, 256, 0, STREAM>>>((const bf16*)probs, dprobs, nrows, H, nq, nk, ld, seed, thresh,
+    bb::launch_pdl(softmax_bwd_kernel<16>, grid, 256, 0, STREAM, (const bf16*)probs, dprobs, nrows, H, nq, nk, ld, seed, thresh,
                                                      scale, out_scale, (bf16*)ds, dbias);
   else
-    softmax_bwd_kernel<32><<<grid, 256, 0, STREAM>>>((const bf16*)probs, dprobs, nrows, H, nq, nk, ld, seed, thresh,
+    bb::launch_pdl(softmax_bwd_kernel<32>, grid, 256, 0, STREAM, (const bf16*)probs, dprobs, nrows, H, nq, nk, ld, seed, thresh,
                                                      scale, out_scale, (bf16*)ds, dbias);
   count_launch();
   return check_launch("softmax_bwd_kernel");
@@ -842,7 +882,7 @@ extern "C" int bb_embed_sum(const int64_t* ids, const float* word, const float* 
   if (ntok <= 0) return 0;
   if (H % 4 != 0) return set_error("bb_embed_sum: H must be a multiple of 4");
   const long long n = ntok * (H / 4);
-  embed_sum_kernel<<<(unsigned)((n + 255) / 256), 256, 0, STREAM>>>(ids, word, pos, type0, ntok, L, H, out);
+  bb::launch_pdl(embed_sum_kernel, (unsigned)((n + 255) / 256), 256, 0, STREAM, ids, word, pos, type0, ntok, L, H, out);
   count_launch();
   return check_launch("embed_sum_kernel");
 }
@@ -850,7 +890,7 @@ extern "C" int bb_embed_scatter_grad(const int64_t* ids, const float* dz, int64_
                                      int64_t padding_idx, float* dword, float* dpos, float* dtype0, void* stream) {
   if (ntok <= 0) return 0;
   const long long n = ntok * H;
-  embed_scatter_grad_kernel<<<(unsigned)((n + 255) / 256), 256, 0, STREAM>>>(ids, dz, ntok, L, H, padding_idx, dword,
+  bb::launch_pdl(embed_scatter_grad_kernel, (unsigned)((n + 255) / 256), 256, 0, STREAM, ids, dz, ntok, L, H, padding_idx, dword,
                                                                              dpos, dtype0);
   count_launch();
   return check_launch("embed_scatter_grad_kernel");
@@ -860,7 +900,7 @@ extern "C" int bb_gather_rows_bf16(const void* in, const int64_t* idx, int64_t n
   if (nout <= 0) return 0;
   if (H % 8 != 0) return set_error("bb_gather_rows_bf16: H must be a multiple of 8");
   const long long n = nout * (H / 8);
-  gather_rows_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, STREAM>>>((const bf16*)in, idx, nout, H, (bf16*)out);
+  bb::launch_pdl(gather_rows_bf16_kernel, (unsigned)((n + 255) / 256), 256, 0, STREAM, (const bf16*)in, idx, nout, H, (bf16*)out);
   count_launch();
   return check_launch("gather_rows_bf16_kernel");
 }
@@ -868,7 +908,7 @@ extern "C" int bb_scatter_add_rows(const void* in_bf16, const int64_t* idx, int6
                                    void* stream) {
   if (nin <= 0) return 0;
   const long long n = nin * H;
-  scatter_add_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, STREAM>>>((const bf16*)in_bf16, idx, nin, H, out_f32);
+  bb::launch_pdl(scatter_add_rows_kernel, (unsigned)((n + 255) / 256), 256, 0, STREAM, (const bf16*)in_bf16, idx, nin, H, out_f32);
   count_launch();
   return check_launch("scatter_add_rows_kernel");
 }
@@ -876,7 +916,7 @@ extern "C" int bb_scatter_add_rows(const void* in_bf16, const int64_t* idx, int6
 extern "C" int bb_softmax_xent(const float* logits, const int64_t* labels, int64_t rows, int V, int64_t ld, float* loss,
                                const float* gscale, void* dlogits, void* stream) {
   if (rows <= 0) return 0;
-  softmax_xent_kernel<<<(unsigned)rows, 256, 0, STREAM>>>(logits, labels, V, ld, loss, gscale, (bf16*)dlogits);
+  bb::launch_pdl(softmax_xent_kernel, (unsigned)rows, 256, 0, STREAM, logits, labels, V, ld, loss, gscale, (bf16*)dlogits);
   count_launch();
   return check_launch("softmax_xent_kernel");
 }

@@ -126,7 +126,7 @@ class GlocalTextPathCMTPreTraining(PreTrainedBase):
 
     def forward(self, batch, task, compute_loss=True):
         batch = defaultdict(lambda: None, batch)   # a copy: the caller's dict is left untouched, as in the reference
-        self.rt.begin(self.training)
+        self.rt.begin(self.training, tag=task)
         batch = self.lift_splat(batch)
         batch = self.drop_feats(batch)
         args = [batch[k] for k in self._BERT_KEYS]
