@@ -200,6 +200,38 @@ typedef struct bb_attn_scores_args {
 int bb_attn_scores(const bb_attn_scores_args* args, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Fused attention core, head dim 64 (csrc/attn_flash.cu): O = dropout(softmax(alpha Q K^T + kmask + bias)) V for
+ * B x H independent (sample, head) problems without materialising scores or probabilities in HBM
+ * (vilmodel.py:103-154 BertSelfAttention, 325-363 BertOutAttention; transformer.py:170-182 panorama encoder).
+ * Element (b, row, h, d) of q / k / v / o / dout / dq / dk / dv is at  ptr + b*X_bs + row*ldX + h*64 + d  (bf16), so
+ * per-head views into packed Q|K|V buffers need no copies.  kmask (B,nk) and bias (B,nq,nk) are additive fp32
+ * (may be NULL); lse (B,H,nq) receives the row log-sum-exp (log2 domain) and is the only tensor saved for backward
+ * besides o; rows whose keys are all -inf give zeros.  Dropout: element (b,h,q,k) is kept iff
+ * hash(seed, ((b*H+h)*nq+q)*nk+k) >= thresh, kept values are scaled by `scale`; backward replays the same mask.
+ * bb_flash_bwd: dsum (B,H,nq) is scratch; dq / dk / dv are overwritten; dbias (B,nq,nk) f32 is accumulated (+=,
+ * summed over heads) when not NULL.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct bb_flash_args {
+  const void* q; const void* k; const void* v; void* o;
+  int64_t q_bs, k_bs, v_bs, o_bs;
+  int32_t ldq, ldk, ldv, ldo;
+  int32_t B, H, nq, nk, dh;
+  float alpha;
+  const float* kmask; const float* bias;
+  float* lse;
+  uint64_t seed; uint32_t thresh; float scale;
+  /* backward only */
+  const void* dout; int64_t do_bs; int32_t lddo; int32_t pad0_;
+  float* dsum;
+  void* dq; void* dk; void* dv;
+  int64_t dq_bs, dk_bs, dv_bs;
+  int32_t lddq, lddk, lddv; int32_t pad1_;
+  float* dbias;
+} bb_flash_args;
+int bb_flash_fwd(const bb_flash_args* args, void* stream);
+int bb_flash_bwd(const bb_flash_args* args, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Native sub-layer executors: ONE call enqueues the whole kernel sequence of a sub-layer on `stream`.
  *   attention sub-layer = LN(dropout(dense(attention(x, c))) + x)     (vilmodel.py:103-166, 325-363)
  *   FFN sub-layer       = LN(dropout(W2 gelu(W1 a + b1) + b2) + a)     (vilmodel.py:168-193)

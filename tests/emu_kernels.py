@@ -74,6 +74,50 @@ def attn_scores_bwd(dctx, ldd, v, ldv, P, B, H, nq, nk, dh, ldp, drop, dbias=Non
     return softmax_bwd(P, dP, B, H, nq, nk, ldp, drop, 1.0 / math.sqrt(dh), dbias)
 
 
+FLASH = True
+
+
+def _heads(t, B, n, H, ld):
+    return _strided(t, (B, H, n, 64), (n * ld, 64, ld, 1))
+
+
+def _flash_probs(q, k, B, H, nq, nk, ldq, ldk, kmask, bias):
+    s = torch.matmul(_heads(q, B, nq, H, ldq).to(F32), _heads(k, B, nk, H, ldk).to(F32).transpose(-1, -2)) * 0.125
+    if kmask is not None:
+        s = s + kmask.view(B, 1, 1, nk)
+    if bias is not None:
+        s = s + bias.view(B, 1, nq, nk)
+    return torch.nan_to_num(torch.softmax(s, -1), nan=0.0)          # rows with every key at -inf give zeros
+
+
+def flash_fwd(q, k, v, B, H, nq, nk, ldq, ldk, ldv, kmask=None, bias=None, drop=(0, 0, 1.0)):
+    assert drop[1] == 0, "emulation runs with dropout disabled"
+    p = _flash_probs(q, k, B, H, nq, nk, ldq, ldk, kmask, bias)
+    o = torch.matmul(p, _heads(v, B, nk, H, ldv).to(F32))          # (B,H,nq,64)
+    return o.permute(0, 2, 1, 3).reshape(B, nq, H * 64).contiguous(), torch.zeros(B, H, nq, dtype=F32)
+
+
+def flash_bwd(q, k, v, o, lse, dout, B, H, nq, nk, ldq, ldk, ldv, kmask=None, bias=None, drop=(0, 0, 1.0), dbias=None,
+              out=None):
+    assert drop[1] == 0
+    Hd = H * 64
+    p = _flash_probs(q, k, B, H, nq, nk, ldq, ldk, kmask, bias)
+    do = _heads(dout, B, nq, H, Hd).to(F32)
+    dp = torch.matmul(do, _heads(v, B, nk, H, ldv).to(F32).transpose(-1, -2))
+    ds = p * (dp - (p * dp).sum(-1, keepdim=True))
+    if dbias is not None:
+        dbias.add_(ds.sum(1))
+    if out is None:
+        dq, dk, dv = torch.zeros(B, nq, Hd, dtype=F32), torch.zeros(B, nk, Hd, dtype=F32), torch.zeros(B, nk, Hd, dtype=F32)
+        lddq = lddk = lddv = Hd
+    else:
+        dq, lddq, dk, lddk, dv, lddv = out
+    _heads(dv, B, nk, H, lddv).copy_(torch.matmul(p.transpose(-1, -2), do))
+    _heads(dq, B, nq, H, lddq).copy_(torch.matmul(ds, _heads(k, B, nk, H, ldk).to(F32)) * 0.125)
+    _heads(dk, B, nk, H, lddk).copy_(torch.matmul(ds.transpose(-1, -2), _heads(q, B, nq, H, ldq).to(F32)) * 0.125)
+    return dq, dk, dv
+
+
 def gemm_profile(enable):
     pass
 
@@ -296,7 +340,7 @@ def softmax_xent(logits, labels, V, ld, want_grad=True):
     return loss, dl
 
 
-_NAMES = ["attn_scores_fwd", "attn_scores_bwd", "gemm_profile", "gemm_profile_records", "native_sublayers", "attn_desc", "ffn_desc", "pano_desc", "sublayer_ws_bytes", "sublayer_fwd", "sublayer_bwd", "gemm", "act_dtype", "drop_params", "launch_count", "reset_launch_count", "bev_lift_index",
+_NAMES = ["flash_fwd", "flash_bwd", "attn_scores_fwd", "attn_scores_bwd", "gemm_profile", "gemm_profile_records", "native_sublayers", "attn_desc", "ffn_desc", "pano_desc", "sublayer_ws_bytes", "sublayer_fwd", "sublayer_bwd", "gemm", "act_dtype", "drop_params", "launch_count", "reset_launch_count", "bev_lift_index",
           "bev_scatter_mean", "bev_scatter_sem", "cast_to_act", "cast_to_f32", "dropout_act", "layernorm_fwd",
           "layernorm_bwd", "colsum", "softmax_fwd", "softmax_bwd", "embed_sum", "embed_scatter_grad", "gather_rows",
           "scatter_add_rows", "gelu_bwd", "relu_bwd", "add_rows", "scale_rows_", "segment_wsum", "segment_wsum_bwd",

@@ -31,4 +31,7 @@ def test_gemm_args_struct_layout():
     assert ctypes.sizeof(_lib.AttnDesc) == 280 and _lib.AttnDesc.seed_attn.offset == 128 and _lib.AttnDesc.dbias.offset == 272
     assert ctypes.sizeof(_lib.PanoDesc) == 320 and _lib.PanoDesc.seed_attn.offset == 136 and _lib.PanoDesc.dbe2.offset == 312
     assert ctypes.sizeof(_lib.FfnDesc) == 184 and _lib.FfnDesc.dbeta.offset == 176
+    F = _lib.FlashArgs
+    assert ctypes.sizeof(F) == 248 and (F.lse.offset, F.dout.offset, F.dsum.offset, F.dq.offset, F.lddq.offset,
+                                        F.dbias.offset) == (120, 144, 168, 176, 224, 240)
     assert _lib.GemmArgs.block_n.offset == 208 and _lib.GemmArgs.add_in.offset == 200  # == sizeof/offsetof in C

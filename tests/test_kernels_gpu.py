@@ -420,6 +420,106 @@ def test_fused_scores_match_unfused_path_and_replay_dropout(K, nq, nk):
     assert rel_l2(dS, dS2) < 6e-3 and rel_l2(db1, db2) < 1e-4
 
 
+def _flash_ref(q, k, v, B, H, nq, nk, ldq, ldk, ldv, kmask, bias, keep=None, scale=1.0):
+    """fp32 torch attention on the same strided views; -> (o (B,nq,H*64), leaf tensors (qh, kh, vh, bias))."""
+    def heads(t, n, ld):
+        return torch.as_strided(t, (B, H, n, 64), (n * ld, 64, ld, 1), t.storage_offset()).float().clone().requires_grad_(True)
+    qh, kh, vh = heads(q, nq, ldq), heads(k, nk, ldk), heads(v, nk, ldv)
+    bl = bias.clone().requires_grad_(True) if bias is not None else None
+    s = qh @ kh.transpose(-1, -2) * 0.125
+    if kmask is not None:
+        s = s + kmask.view(B, 1, 1, nk)
+    if bl is not None:
+        s = s + bl.view(B, 1, nq, nk)
+    p = torch.softmax(s, -1)
+    pd = p if keep is None else p * keep * scale
+    o = (pd @ vh).permute(0, 2, 1, 3).reshape(B, nq, H * 64)
+    return o, p, (qh, kh, vh, bl)
+
+
+@pytest.mark.parametrize("nq,nk,cross", [(441, 441, False), (80, 80, False), (36, 36, False), (23, 23, False),
+                                         (23, 80, True), (441, 80, True), (80, 441, True), (130, 200, True), (64, 128, True)])
+def test_flash_attention_matches_fp32_reference(K, nq, nk, cross):
+    """bb_flash_fwd / bb_flash_bwd (csrc/attn_flash.cu) vs fp32 torch attention + autograd on the same packed
+    Q|K|V views: key masks (-10000 and -inf), additive bias and its gradient, ragged tile tails."""
+    B, H, Hd = 2, 12, 768
+    if not cross:
+        qkv = rnd(B * nq, 3 * Hd, scale=0.8).cuda()
+        q, k, v, ldq, ldk, ldv = qkv, qkv[:, Hd:], qkv[:, 2 * Hd:], 3 * Hd, 3 * Hd, 3 * Hd
+    else:
+        q = rnd(B * nq, Hd, scale=0.8).cuda()
+        kv = rnd(B * nk, 2 * Hd, scale=0.8, seed=1).cuda()
+        k, v, ldq, ldk, ldv = kv, kv[:, Hd:], Hd, 2 * Hd, 2 * Hd
+    kmask = torch.zeros(B, nk)
+    kmask[1, nk // 2:] = -10000.0
+    kmask[0, -3:] = float("-inf")
+    kmask = kmask.cuda()
+    bias = (torch.randn(B, nq, nk) * 0.3).cuda()
+    dout = rnd(B, nq, Hd, scale=0.5, seed=2).cuda()
+    o, lse = K.flash_fwd(q, k, v, B, H, nq, nk, ldq, ldk, ldv, kmask, bias)
+    ro, _, (qh, kh, vh, bl) = _flash_ref(q, k, v, B, H, nq, nk, ldq, ldk, ldv, kmask, bias)
+    assert rel_l2(o, ro) < 6e-3
+    ro.backward(dout.float())
+    dbias = torch.zeros(B, nq, nk, device="cuda")
+    dq, dk, dv = K.flash_bwd(q, k, v, o, lse, dout, B, H, nq, nk, ldq, ldk, ldv, kmask, bias, dbias=dbias)
+
+    def unheads(t, n):
+        return t.permute(0, 2, 1, 3).reshape(B, n, Hd)
+    assert rel_l2(dq, unheads(qh.grad, nq)) < 1.2e-2
+    assert rel_l2(dk, unheads(kh.grad, nk)) < 1.2e-2
+    assert rel_l2(dv, unheads(vh.grad, nk)) < 1.2e-2
+    assert rel_l2(dbias, bl.grad) < 1.2e-2
+    assert torch.isfinite(o.float()).all() and torch.isfinite(dq.float()).all() and torch.isfinite(dk.float()).all()
+    # without mask / bias, written into packed views (the executors' layout)
+    o2, lse2 = K.flash_fwd(q, k, v, B, H, nq, nk, ldq, ldk, ldv)
+    ro2, _, (qh, kh, vh, _) = _flash_ref(q, k, v, B, H, nq, nk, ldq, ldk, ldv, None, None)
+    assert rel_l2(o2, ro2) < 6e-3
+    ro2.backward(dout.float())
+    dpack = torch.zeros(B * nk, 2 * Hd, dtype=BF, device="cuda")
+    dqo = torch.zeros(B * nq, Hd, dtype=BF, device="cuda")
+    K.flash_bwd(q, k, v, o2, lse2, dout, B, H, nq, nk, ldq, ldk, ldv, out=(dqo, Hd, dpack, 2 * Hd, dpack[:, Hd:], 2 * Hd))
+    assert rel_l2(dqo.view(B, nq, Hd), unheads(qh.grad, nq)) < 1.2e-2
+    assert rel_l2(dpack[:, :Hd].reshape(B, nk, Hd), unheads(kh.grad, nk)) < 1.2e-2
+    assert rel_l2(dpack[:, Hd:].reshape(B, nk, Hd), unheads(vh.grad, nk)) < 1.2e-2
+
+
+def test_flash_attention_dropout_is_replayed_in_backward(K):
+    """With V = identity per head, O is the dropped probability matrix itself: the kept fraction matches p, kept
+    entries are P / (1-p), and backward with the same seed equals autograd through that exact mask."""
+    B, H, Hd, nq, nk = 2, 12, 768, 100, 64
+    q = rnd(B * nq, Hd, scale=0.8).cuda()
+    kv = rnd(B * nk, 2 * Hd, scale=0.8, seed=1).cuda()
+    eye = torch.eye(64).repeat(B, 1, H).view(B * nk, Hd)            # V_h = I for every head
+    kv[:, Hd:] = eye.to(BF).cuda()
+    k, v = kv, kv[:, Hd:]
+    th, sc = K.drop_params(0.1)
+    drop = (977, th, sc)
+    o, lse = K.flash_fwd(q, k, v, B, H, nq, nk, Hd, 2 * Hd, 2 * Hd, drop=drop)
+    o_nodrop, _ = K.flash_fwd(q, k, v, B, H, nq, nk, Hd, 2 * Hd, 2 * Hd)
+    pd = o.float().view(B, nq, H, 64).permute(0, 2, 1, 3)           # (B,H,nq,nk)
+    p = o_nodrop.float().view(B, nq, H, 64).permute(0, 2, 1, 3)
+    big = p > 1e-3
+    keep = (pd != 0)
+    frac = 1.0 - keep[big].float().mean().item()
+    assert abs(frac - 0.1) < 0.01, frac
+    assert rel_l2(pd[big & keep], p[big & keep] * sc) < 1e-2
+    o_b, _ = K.flash_fwd(q, k, v, B, H, nq, nk, Hd, 2 * Hd, 2 * Hd, drop=(978, th, sc))
+    assert not torch.equal(o, o_b) and torch.equal(o, K.flash_fwd(q, k, v, B, H, nq, nk, Hd, 2 * Hd, 2 * Hd, drop=drop)[0])
+    # backward through the same mask (entries with p <= 1e-3 that were dropped are indistinguishable: treat as kept,
+    # their contribution is below the tolerance)
+    mask = (keep | ~big).float()
+    dout = rnd(B, nq, Hd, scale=0.5, seed=2).cuda()
+    ro, _, (qh, kh, vh, _) = _flash_ref(q, k, v, B, H, nq, nk, Hd, 2 * Hd, 2 * Hd, None, None, keep=mask, scale=sc)
+    ro.backward(dout.float())
+    dq, dk, dv = K.flash_bwd(q, k, v, o, lse, dout, B, H, nq, nk, Hd, 2 * Hd, 2 * Hd, drop=drop)
+
+    def unheads(t, n):
+        return t.permute(0, 2, 1, 3).reshape(B, n, Hd)
+    assert rel_l2(dq, unheads(qh.grad, nq)) < 2e-2
+    assert rel_l2(dk, unheads(kh.grad, nk)) < 2e-2
+    assert rel_l2(dv, unheads(vh.grad, nk)) < 2e-2
+
+
 def test_native_pano_layer_equals_python_composition(K, monkeypatch):
     import bevbert_b200.blocks as Bk
     torch.manual_seed(1)

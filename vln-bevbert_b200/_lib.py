@@ -45,6 +45,16 @@ class AttnScoresArgs(C.Structure):
         [(n, c_void_p) for n in ("P", "Pd", "Pin", "dS", "dbias")]
 
 
+class FlashArgs(C.Structure):
+    """struct bb_flash_args (include/bevbert_b200.h)."""
+    _fields_ = [(n, c_void_p) for n in ("q", "k", "v", "o")] + [(n, c_i64) for n in ("q_bs", "k_bs", "v_bs", "o_bs")] + \
+        [(n, c_i32) for n in ("ldq", "ldk", "ldv", "ldo", "B", "H", "nq", "nk", "dh")] + [("alpha", c_float)] + \
+        [("kmask", c_void_p), ("bias", c_void_p), ("lse", c_void_p), ("seed", c_u64), ("thresh", c_u32), ("scale", c_float)] + \
+        [("dout", c_void_p), ("do_bs", c_i64), ("lddo", c_i32), ("pad0_", c_i32), ("dsum", c_void_p)] + \
+        [(n, c_void_p) for n in ("dq", "dk", "dv")] + [(n, c_i64) for n in ("dq_bs", "dk_bs", "dv_bs")] + \
+        [(n, c_i32) for n in ("lddq", "lddk", "lddv", "pad1_")] + [("dbias", c_void_p)]
+
+
 class AttnDesc(C.Structure):
     """struct bb_attn_desc (include/bevbert_b200.h)."""
     _fields_ = [(n, c_i32) for n in ("B", "nq", "nk", "Hd", "heads", "cross", "want_dbias")] + [("eps", c_float)] + \
@@ -114,6 +124,8 @@ _SIGNATURES = {
     "bb_add_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_void_p]),
     "bb_axpy_f32_from_bf16": (c_int, [c_void_p, c_void_p, c_i64, c_void_p]),
     "bb_attn_scores": (c_int, [C.POINTER(AttnScoresArgs), c_void_p]),
+    "bb_flash_fwd": (c_int, [C.POINTER(FlashArgs), c_void_p]),
+    "bb_flash_bwd": (c_int, [C.POINTER(FlashArgs), c_void_p]),
     "bb_attn_ws_bytes": (c_int, [C.POINTER(AttnDesc), C.POINTER(c_i64), C.POINTER(c_i64)]),
     "bb_attn_fwd": (c_int, [C.POINTER(AttnDesc), c_void_p]),
     "bb_attn_bwd": (c_int, [C.POINTER(AttnDesc), c_void_p]),

@@ -221,6 +221,10 @@ def attn_core_fwd(st, q, ldq, k, ldk, v, ldv, B, H, nq, nk, dh, kmask, bias, dro
     """softmax(Q K^T / sqrt(dh) + kmask + bias) V for every (sample, head).  q/k/v are views whose first
     element is (sample 0, row 0, head 0, dim 0); rows are ld* apart, heads dh apart.  -> ctx (B*nq, H*dh)."""
     ldp = _round8(nk)
+    if K.FLASH and dh == 64:
+        ctx, lse = K.flash_fwd(q, k, v, B, H, nq, nk, ldq, ldk, ldv, kmask, bias, drop)
+        st.update(lse=lse, fctx=ctx, geo=(B, H, nq, nk, dh, ldp), adrop=drop, amask=(kmask, bias))
+        return ctx.view(B * nq, H * dh)
     if nk <= K.FUSED_SCORES_MAX_KEYS and dh == 64:
         P, Pd = K.attn_scores_fwd(q, ldq, k, ldk, B, H, nq, nk, dh, ldp, kmask, bias, drop)
     else:
@@ -239,6 +243,11 @@ def attn_core_fwd(st, q, ldq, k, ldk, v, ldv, B, H, nq, nk, dh, kmask, bias, dro
 def attn_core_bwd(st, dctx, q, ldq, k, ldk, v, ldv, dq, lddq, dk, lddk, dv, lddv, dbias=None):
     """Writes dQ / dK / dV into the given views (same geometry as q/k/v)."""
     B, H, nq, nk, dh, ldp = st["geo"]
+    if "lse" in st:
+        kmask, bias = st["amask"]
+        K.flash_bwd(q, k, v, st["fctx"], st["lse"], dctx, B, H, nq, nk, ldq, ldk, ldv, kmask, bias, st["adrop"], dbias,
+                    out=(dq, lddq, dk, lddk, dv, lddv))
+        return
     P, Pd, drop = st["P"], st["Pd"], st["adrop"]
     HD = H * dh
     # dV = Pd^T dctx

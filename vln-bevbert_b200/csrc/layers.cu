@@ -28,11 +28,20 @@ static inline int fused_max_keys() {
   return v;
 }
 static inline int round8(int n) { return (n + 7) / 8 * 8; }
+// fused attention core (attn_flash.cu) for head dim 64; BB_FLASH=0 selects the unfused GEMM + softmax sequence
+static inline bool flash_on(const bb_attn_desc* d) {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("BB_FLASH");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v && d->Hd / d->heads == 64;
+}
 
 struct AttnLayout {
   int ldp;
-  int64_t qkv, q, kv, S, P, Pd, ctx, ao, mean, rstd, fwd_bytes;
-  int64_t dao, dres, dctx, dqkv, dq, dkv, dP, dS, bwd_bytes;
+  int64_t qkv, q, kv, S, P, Pd, lse, ctx, ao, mean, rstd, fwd_bytes;
+  int64_t dao, dres, dctx, dqkv, dq, dkv, dP, dS, dsum, bwd_bytes;
 };
 
 static AttnLayout attn_layout(const bb_attn_desc* d) {
@@ -44,9 +53,15 @@ static AttnLayout attn_layout(const bb_attn_desc* d) {
   int64_t o = 0;
   if (!d->cross) { L.qkv = o; o += al(Mq * 3 * Hd * 2); }
   else { L.q = o; o += al(Mq * Hd * 2); L.kv = o; o += al(Mk * 2 * Hd * 2); }
-  L.S = o; if (d->nk > fused_max_keys()) o += al(pn * 4);   // fp32 scores only on the unfused path
-  L.P = o; o += al(pn * 2);
-  if (d->th_attn) { L.Pd = o; o += al(pn * 2); } else L.Pd = L.P;
+  const bool flash = flash_on(d);
+  const int64_t rows = (int64_t)d->B * d->heads * d->nq;
+  if (flash) {
+    L.lse = o; o += al(rows * 4);                             // the only attention state saved for backward
+  } else {
+    L.S = o; if (d->nk > fused_max_keys()) o += al(pn * 4);   // fp32 scores only on the unfused path
+    L.P = o; o += al(pn * 2);
+    if (d->th_attn) { L.Pd = o; o += al(pn * 2); } else L.Pd = L.P;
+  }
   L.ctx = o; o += al(Mq * Hd * 2);
   L.ao = o; o += al(Mq * Hd * 2);
   L.mean = o; o += al(Mq * 4);
@@ -58,8 +73,12 @@ static AttnLayout attn_layout(const bb_attn_desc* d) {
   L.dctx = o; o += al(Mq * Hd * 2);
   if (!d->cross) { L.dqkv = o; o += al(Mq * 3 * Hd * 2); }
   else { L.dq = o; o += al(Mq * Hd * 2); L.dkv = o; o += al(Mk * 2 * Hd * 2); }
-  L.dP = o; if (d->nk > fused_max_keys()) o += al(pn * 4);
-  L.dS = o; o += al(pn * 2);
+  if (flash) {
+    L.dsum = o; o += al(rows * 4);
+  } else {
+    L.dP = o; if (d->nk > fused_max_keys()) o += al(pn * 4);
+    L.dS = o; o += al(pn * 2);
+  }
   L.bwd_bytes = o;
   return L;
 }
@@ -116,6 +135,17 @@ static int lin_bwd_dw(const void* dy, const void* x, float* out, int64_t M, int 
 static int attn_core_fwd(const bb_attn_desc* d, const AttnLayout& L, const void* q, int ldq, const void* k, int ldk,
                          const void* v, int ldv, void* stream) {
   const int B = d->B, H = d->heads, nq = d->nq, nk = d->nk, dh = d->Hd / d->heads, ldp = L.ldp;
+  if (flash_on(d)) {
+    bb_flash_args f;
+    memset(&f, 0, sizeof(f));
+    f.q = q; f.k = k; f.v = v; f.o = at(d->ws, L.ctx);
+    f.q_bs = (int64_t)nq * ldq; f.k_bs = (int64_t)nk * ldk; f.v_bs = (int64_t)nk * ldv; f.o_bs = (int64_t)nq * d->Hd;
+    f.ldq = ldq; f.ldk = ldk; f.ldv = ldv; f.ldo = d->Hd;
+    f.B = B; f.H = H; f.nq = nq; f.nk = nk; f.dh = dh; f.alpha = 1.0f / sqrtf((float)dh);
+    f.kmask = d->kmask; f.bias = d->bias; f.lse = reinterpret_cast<float*>(at(d->ws, L.lse));
+    f.seed = d->seed_attn; f.thresh = d->th_attn; f.scale = d->sc_attn;
+    return bb_flash_fwd(&f, stream);
+  }
   bb_gemm_args g;
   if (nk <= fused_max_keys() && dh == 64) {
     bb_attn_scores_args s;
@@ -149,6 +179,23 @@ static int attn_core_bwd(const bb_attn_desc* d, const AttnLayout& L, const void*
                          void* stream) {
   const int B = d->B, H = d->heads, nq = d->nq, nk = d->nk, dh = d->Hd / d->heads, ldp = L.ldp, HD = d->Hd;
   const void* dctx = at(d->gws, L.dctx);
+  if (flash_on(d)) {
+    bb_flash_args f;
+    memset(&f, 0, sizeof(f));
+    f.q = q; f.k = k; f.v = v; f.o = const_cast<char*>(at(static_cast<const void*>(d->ws), L.ctx));
+    f.q_bs = (int64_t)nq * ldq; f.k_bs = (int64_t)nk * ldk; f.v_bs = (int64_t)nk * ldv; f.o_bs = (int64_t)nq * HD;
+    f.ldq = ldq; f.ldk = ldk; f.ldv = ldv; f.ldo = HD;
+    f.B = B; f.H = H; f.nq = nq; f.nk = nk; f.dh = dh; f.alpha = 1.0f / sqrtf((float)dh);
+    f.kmask = d->kmask; f.bias = d->bias; f.lse = reinterpret_cast<float*>(at(d->ws, L.lse));
+    f.seed = d->seed_attn; f.thresh = d->th_attn; f.scale = d->sc_attn;
+    f.dout = dctx; f.do_bs = (int64_t)nq * HD; f.lddo = HD;
+    f.dsum = reinterpret_cast<float*>(at(d->gws, L.dsum));
+    f.dq = dq; f.dq_bs = (int64_t)nq * lddq; f.lddq = lddq;
+    f.dk = dk; f.dk_bs = (int64_t)nk * lddk; f.lddk = lddk;
+    f.dv = dv; f.dv_bs = (int64_t)nk * lddv; f.lddv = lddv;
+    f.dbias = d->want_dbias ? d->dbias : nullptr;
+    return bb_flash_bwd(&f, stream);
+  }
   const int64_t ps1 = (int64_t)nq * ldp, ps2 = (int64_t)H * nq * ldp;
   bb_gemm_args g;
   // dV = Pd^T dctx
@@ -347,9 +394,17 @@ static PanoLayout pano_layout(const bb_pano_desc* d) {
   L.r1 = o; o += al(M * 4);
   L.qkv = o; o += al(M * 3 * Hd * 2);
   L.A.ldp = ldp;
-  L.A.S = o; if (!fused) o += al(pn * 4);
-  L.A.P = o; o += al(pn * 2);
-  if (d->th_attn) { L.A.Pd = o; o += al(pn * 2); } else L.A.Pd = L.A.P;
+  bb_attn_desc probe;
+  pano_attn_desc(d, &probe);
+  const bool flash = flash_on(&probe);
+  const int64_t rows = (int64_t)d->N * d->heads * d->V;
+  if (flash) {
+    L.A.lse = o; o += al(rows * 4);
+  } else {
+    L.A.S = o; if (!fused) o += al(pn * 4);
+    L.A.P = o; o += al(pn * 2);
+    if (d->th_attn) { L.A.Pd = o; o += al(pn * 2); } else L.A.Pd = L.A.P;
+  }
   L.A.ctx = o; o += al(M * Hd * 2);
   L.x1 = o; o += al(M * Hd * 2);
   L.h2 = o; o += al(M * Hd * 2);
@@ -367,8 +422,12 @@ static PanoLayout pano_layout(const bb_pano_desc* d) {
   L.d1g = o; o += al(M * Hd * 2);
   L.A.dctx = o; o += al(M * Hd * 2);
   L.dqkv = o; o += al(M * 3 * Hd * 2);
-  L.A.dP = o; if (!fused) o += al(pn * 4);
-  L.A.dS = o; o += al(pn * 2);
+  if (flash) {
+    L.A.dsum = o; o += al(rows * 4);
+  } else {
+    L.A.dP = o; if (!fused) o += al(pn * 4);
+    L.A.dS = o; o += al(pn * 2);
+  }
   L.dh1 = o; o += al(M * Hd * 2);
   L.dxln = o; o += al(M * Hd * 2);
   L.bwd_bytes = o;

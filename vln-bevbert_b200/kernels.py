@@ -182,6 +182,56 @@ def attn_scores_bwd(dctx, ldd, v, ldv, P, B, H, nq, nk, dh, ldp, drop, dbias=Non
     return dS
 
 
+NO_DROP = (0, 0, 1.0)
+FLASH = __import__('os').environ.get('BB_FLASH', '1') != '0'     # fused attention core (csrc/attn_flash.cu), head dim 64
+
+
+def _flash_args(q, k, v, o, lse, B, H, nq, nk, ldq, ldk, ldv, ldo, kmask, bias, drop):
+    a = _lib.FlashArgs()
+    a.q, a.k, a.v, a.o = q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr()
+    a.q_bs, a.k_bs, a.v_bs, a.o_bs = nq * ldq, nk * ldk, nk * ldv, nq * ldo
+    a.ldq, a.ldk, a.ldv, a.ldo = ldq, ldk, ldv, ldo
+    a.B, a.H, a.nq, a.nk, a.dh = B, H, nq, nk, 64
+    a.alpha = 0.125
+    a.kmask, a.bias, a.lse = _p(kmask), _p(bias), lse.data_ptr()
+    a.seed, a.thresh, a.scale = drop
+    return a
+
+
+def flash_fwd(q, k, v, B, H, nq, nk, ldq, ldk, ldv, kmask=None, bias=None, drop=NO_DROP):
+    """fused attention core (bb_flash_fwd): q/k/v are bf16 tensors whose data_ptr is element (0,0,0,0) of the
+    (B, rows, H, 64) view with row stride ld*; -> (o (B,nq,H*64) bf16, lse (B,H,nq) f32)."""
+    for t, n in ((q, "q"), (k, "k"), (v, "v")):
+        _req(t, BF16, n)
+    o = torch.empty(B, nq, H * 64, dtype=BF16, device=q.device)
+    lse = torch.empty(B, H, nq, dtype=torch.float32, device=q.device)
+    a = _flash_args(q, k, v, o, lse, B, H, nq, nk, ldq, ldk, ldv, H * 64, kmask, bias, drop)
+    _lib.check(_lib.load().bb_flash_fwd(C.byref(a), _stream()), "bb_flash_fwd")
+    return o, lse
+
+
+def flash_bwd(q, k, v, o, lse, dout, B, H, nq, nk, ldq, ldk, ldv, kmask=None, bias=None, drop=NO_DROP, dbias=None,
+              out=None):
+    """backward of flash_fwd: -> (dq (B,nq,H*64), dk (B,nk,H*64), dv (B,nk,H*64)) bf16; dbias (B,nq,nk) f32 += .
+    out = (dq, lddq, dk, lddk, dv, lddv) writes into existing views with the geometry of q / k / v instead."""
+    Hd = H * 64
+    a = _flash_args(q, k, v, o, lse, B, H, nq, nk, ldq, ldk, ldv, Hd, kmask, bias, drop)
+    if out is None:
+        dq = torch.empty(B, nq, Hd, dtype=BF16, device=q.device)
+        dk = torch.empty(B, nk, Hd, dtype=BF16, device=q.device)
+        dv = torch.empty(B, nk, Hd, dtype=BF16, device=q.device)
+        lddq = lddk = lddv = Hd
+    else:
+        dq, lddq, dk, lddk, dv, lddv = out
+    dsum = torch.empty(B, H, nq, dtype=torch.float32, device=q.device)
+    a.dout, a.do_bs, a.lddo, a.dsum = dout.data_ptr(), nq * Hd, Hd, dsum.data_ptr()
+    a.dq, a.dk, a.dv = dq.data_ptr(), dk.data_ptr(), dv.data_ptr()
+    a.dq_bs, a.dk_bs, a.dv_bs, a.lddq, a.lddk, a.lddv = nq * lddq, nk * lddk, nk * lddv, lddq, lddk, lddv
+    a.dbias = _p(dbias)
+    _lib.check(_lib.load().bb_flash_bwd(C.byref(a), _stream()), "bb_flash_bwd")
+    return dq, dk, dv
+
+
 # ---------------------------------------------------------------------------------------------- BEV
 def bev_lift_index(depths, T_c2w, S_w2c, T_w2c, map_dim, map_res, depth_scale=10.0, fx=7.0, fy=7.0, cx=7.0, cy=7.0,
                    y_clip=0.5, want_pc=False):
