@@ -206,8 +206,9 @@ int bb_attn_scores(const bb_attn_scores_args* args, void* stream);
  * Element (b, row, h, d) of q / k / v / o / dout / dq / dk / dv is at  ptr + b*X_bs + row*ldX + h*64 + d  (bf16), so
  * per-head views into packed Q|K|V buffers need no copies.  kmask (B,nk) and bias (B,nq,nk) are additive fp32
  * (may be NULL); lse (B,H,nq) receives the row log-sum-exp (log2 domain) and is the only tensor saved for backward
- * besides o; rows whose keys are all -inf give zeros.  Dropout: element (b,h,q,k) is kept iff
- * hash(seed, ((b*H+h)*nq+q)*nk+k) >= thresh, kept values are scaled by `scale`; backward replays the same mask.
+ * besides o; rows whose keys are all -inf give zeros.  Dropout: element (b,h,q,k) is kept iff a 16-bit half of
+ * mix(hash(seed, (b*H+h)*nq+q), k/2) is >= thresh >> 16 (one row hash, one mix per pair of adjacent keys); kept
+ * values are scaled by `scale`; backward replays the same mask.
  * bb_flash_bwd: dsum (B,H,nq) is scratch; dq / dk / dv are overwritten; dbias (B,nq,nk) f32 is accumulated (+=,
  * summed over heads) when not NULL.
  * ------------------------------------------------------------------------------------------- */

@@ -8,7 +8,14 @@ BF = torch.bfloat16
 B, H, Hd = 32, 12, 768
 
 
+ONLY = os.environ.get("ATTN_ONLY")
+
+
 def timeit(fn, n=20):
+    if ONLY:
+        fn()
+        torch.cuda.synchronize()
+        return 1.0
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
@@ -25,6 +32,8 @@ for name, b, nq, nk, cross, p in [("bev self 441", B, 441, 441, False, 0.1), ("l
                                   ("bev->lang 441x80", B, 441, 80, True, 0.1), ("lang->bev 80x441", B, 80, 441, True, 0.1),
                                   ("gmap self 23", B, 23, 23, False, 0.1), ("gmap->lang 23x80", B, 23, 80, True, 0.1),
                                   ("pano 36 x179", 179, 36, 36, False, 0.1), ("bev self 441 p=0", B, 441, 441, False, 0.0)]:
+    if ONLY and not name.startswith(ONLY):
+        continue
     if not cross:
         qkv = (torch.randn(b * nq, 3 * Hd, device="cuda") * 0.5).to(BF)
         q, k, v, ldq, ldk, ldv = qkv, qkv[:, Hd:], qkv[:, 2 * Hd:], 3 * Hd, 3 * Hd, 3 * Hd

@@ -161,6 +161,20 @@ __device__ __forceinline__ void store_rows(uint32_t tile, uint8_t* tile_ptr, con
   (void)tile;
 }
 
+// Dropout decisions for the attention probabilities: one full hash per (sample, head, query) row, then one cheap
+// two-round mix per PAIR of adjacent keys whose 16-bit halves decide the two elements (keep iff half >= thresh >> 16).
+// Forward and both backward kernels evaluate the same function of (seed, b, h, q, k).
+__device__ __forceinline__ uint32_t row_hash(uint64_t seed, int64_t row) { return rng_u32(seed, (uint64_t)row); }
+__device__ __forceinline__ uint32_t mix_pair(uint32_t rowhash, uint32_t pair) {
+  uint32_t x = rowhash ^ (pair * 0x9E3779B1u);
+  x ^= x >> 15;
+  x *= 0x2C1B3C6Du;
+  x ^= x >> 12;
+  x *= 0x297A2D39u;
+  x ^= x >> 15;
+  return x;
+}
+
 __device__ __forceinline__ float quad_max(float v) {
   v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
   return fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
@@ -170,68 +184,89 @@ __device__ __forceinline__ float quad_sum(float v) {
   return v + __shfl_xor_sync(0xffffffffu, v, 2);
 }
 
+// log2-domain additive key mask of tile j (kmask * log2e; -inf beyond nk) -> smem, one float per key
+__device__ __forceinline__ void stage_kmask(float* km, const Params& p, int b, int j, int tid) {
+  if (tid < BN) {
+    const int col = j * BN + tid;
+    km[tid] = col < p.nk ? (p.kmask ? p.kmask[(int64_t)b * p.nk + col] * LOG2E : 0.f) : -INFINITY;
+  }
+}
 // s (C layout: rows r0 / r0+8 = queries, cols = keys of tile j) -> log2-domain logits (alpha s + kmask + bias) log2e
-__device__ __forceinline__ void logits_qk(float (&s)[8][4], const Params& p, int b, int r0, int j, int t) {
-  const float* km = p.kmask ? p.kmask + (int64_t)b * p.nk : nullptr;
-  const float* bs0 = (p.bias && r0 < p.nq) ? p.bias + ((int64_t)b * p.nq + r0) * p.nk : nullptr;
-  const float* bs1 = (p.bias && r0 + 8 < p.nq) ? p.bias + ((int64_t)b * p.nq + r0 + 8) * p.nk : nullptr;
+__device__ __forceinline__ void logits_qk(float (&s)[8][4], const Params& p, const float* km, int b, int r0, int j, int t) {
+  const float a2 = p.alpha * LOG2E;
 #pragma unroll
   for (int nb = 0; nb < 8; ++nb) {
+    const float2 m = *reinterpret_cast<const float2*>(km + nb * 8 + 2 * t);
+    s[nb][0] = fmaf(s[nb][0], a2, m.x);
+    s[nb][1] = fmaf(s[nb][1], a2, m.y);
+    s[nb][2] = fmaf(s[nb][2], a2, m.x);
+    s[nb][3] = fmaf(s[nb][3], a2, m.y);
+  }
+  if (p.bias) {   // graph bias of the global map encoder only (few, small problems)
+    const float* bs0 = r0 < p.nq ? p.bias + ((int64_t)b * p.nq + r0) * p.nk : nullptr;
+    const float* bs1 = r0 + 8 < p.nq ? p.bias + ((int64_t)b * p.nq + r0 + 8) * p.nk : nullptr;
 #pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      const int col = j * BN + nb * 8 + 2 * t + e;
-      if (col < p.nk) {
-        const float m = km ? km[col] : 0.f;
-        s[nb][e] = (s[nb][e] * p.alpha + m + (bs0 ? bs0[col] : 0.f)) * LOG2E;
-        s[nb][2 + e] = (s[nb][2 + e] * p.alpha + m + (bs1 ? bs1[col] : 0.f)) * LOG2E;
-      } else {
-        s[nb][e] = -INFINITY;
-        s[nb][2 + e] = -INFINITY;
+    for (int nb = 0; nb < 8; ++nb) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int col = j * BN + nb * 8 + 2 * t + e;
+        if (col < p.nk) {
+          if (bs0) s[nb][e] = fmaf(bs0[col], LOG2E, s[nb][e]);
+          if (bs1) s[nb][2 + e] = fmaf(bs1[col], LOG2E, s[nb][2 + e]);
+        }
       }
     }
   }
 }
 
 // ------------------------------------------------------------------------------------------------ forward
-__global__ void __launch_bounds__(NT) flash_fwd_kernel(const Params p) {
-  __shared__ __align__(128) uint8_t smem[5 * TILE_BYTES];
+__global__ void __launch_bounds__(NT, 4) flash_fwd_kernel(const Params p) {
+  __shared__ __align__(128) uint8_t smem[4 * TILE_BYTES];
+  __shared__ __align__(16) float s_km[2][BN];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gq = lane >> 2, t = lane & 3;
   const int q0 = blockIdx.x * BM, h = blockIdx.y, b = blockIdx.z;
-  const uint32_t sQ = smem_u32(smem), sK = sQ + TILE_BYTES, sV = sQ + 3 * TILE_BYTES;
+  const uint32_t sK = smem_u32(smem), sV = sK + 2 * TILE_BYTES, sQ = sK + TILE_BYTES;   // Q staged in K's 2nd buffer
   pdl_wait();
   pdl_trigger();
   const bf16* kg = p.k + b * p.k_bs + h * DH;
   const bf16* vg = p.v + b * p.v_bs + h * DH;
   const int ntile = (p.nk + BN - 1) / BN;
+  const bool active = q0 + warp * 16 < p.nq;   // warps whose 16 rows are all padding only help with the loads
   load_tile(sQ, p.q + b * p.q_bs + (int64_t)q0 * p.ldq + h * DH, p.ldq, p.nq - q0, tid);
   load_tile(sK, kg, p.ldk, p.nk, tid);
   load_tile(sV, vg, p.ldv, p.nk, tid);
+  stage_kmask(s_km[0], p, b, 0, tid);
   cp_async_commit();
 
   const int r0 = q0 + warp * 16 + gq;   // this thread's rows: r0 and r0 + 8
-  const int64_t rng0 = (((int64_t)b * p.H + h) * p.nq + r0) * p.nk, rng1 = rng0 + 8 * (int64_t)p.nk;
+  const uint32_t t16 = p.thresh >> 16;
+  const uint32_t rh0 = row_hash(p.seed, ((int64_t)b * p.H + h) * p.nq + r0), rh1 = row_hash(p.seed, ((int64_t)b * p.H + h) * p.nq + r0 + 8);
   float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
   float o[8][4];
 #pragma unroll
   for (int i = 0; i < 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
   uint32_t qf[4][4];
+  cp_async_wait<0>();
+  __syncthreads();
+  load_a_frags(sQ, warp * 16, lane, qf);
 
   for (int j = 0; j < ntile; ++j) {
     const int buf = j & 1;
+    cp_async_wait<0>();
+    __syncthreads();   // tile j has landed; every warp is done with tile j-1 (and with Q), so the other buffer is free
     if (j + 1 < ntile) {
       load_tile(sK + (buf ^ 1) * TILE_BYTES, kg + (int64_t)(j + 1) * BN * p.ldk, p.ldk, p.nk - (j + 1) * BN, tid);
       load_tile(sV + (buf ^ 1) * TILE_BYTES, vg + (int64_t)(j + 1) * BN * p.ldv, p.ldv, p.nk - (j + 1) * BN, tid);
+      stage_kmask(s_km[buf ^ 1], p, b, j + 1, tid);
+      cp_async_commit();
     }
-    cp_async_commit();
-    cp_async_wait<1>();
-    __syncthreads();
-    if (j == 0) load_a_frags(sQ, warp * 16, lane, qf);
+    if (!active) continue;
 
     float s[8][4];
 #pragma unroll
     for (int i = 0; i < 8; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
     mma_a_tT(s, qf, sK + buf * TILE_BYTES, lane);
-    logits_qk(s, p, b, r0, j, t);
+    logits_qk(s, p, s_km[buf], b, r0, j, t);
 
     float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
@@ -247,19 +282,21 @@ __global__ void __launch_bounds__(NT) flash_fwd_kernel(const Params p) {
     float ps0 = 0.f, ps1 = 0.f;
 #pragma unroll
     for (int nb = 0; nb < 8; ++nb) {
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        float p0 = ex2(s[nb][e] - ms0), p1 = ex2(s[nb][2 + e] - ms1);
-        ps0 += p0;
-        ps1 += p1;
-        if (p.thresh) {
-          const int col = j * BN + nb * 8 + 2 * t + e;
-          p0 = drop_keep(p.seed, rng0 + col, p.thresh) ? p0 * p.scale : 0.f;
-          p1 = drop_keep(p.seed, rng1 + col, p.thresh) ? p1 * p.scale : 0.f;
-        }
-        s[nb][e] = p0;
-        s[nb][2 + e] = p1;
+      float p00 = ex2(s[nb][0] - ms0), p01 = ex2(s[nb][1] - ms0), p10 = ex2(s[nb][2] - ms1), p11 = ex2(s[nb][3] - ms1);
+      ps0 += p00 + p01;
+      ps1 += p10 + p11;
+      if (p.thresh) {
+        const uint32_t pair = j * (BN / 2) + nb * 4 + t;
+        const uint32_t x0 = mix_pair(rh0, pair), x1 = mix_pair(rh1, pair);
+        p00 = (x0 & 0xFFFFu) >= t16 ? p00 * p.scale : 0.f;
+        p01 = (x0 >> 16) >= t16 ? p01 * p.scale : 0.f;
+        p10 = (x1 & 0xFFFFu) >= t16 ? p10 * p.scale : 0.f;
+        p11 = (x1 >> 16) >= t16 ? p11 * p.scale : 0.f;
       }
+      s[nb][0] = p00;
+      s[nb][1] = p01;
+      s[nb][2] = p10;
+      s[nb][3] = p11;
     }
     l0 = l0 * c0 + ps0;
     l1 = l1 * c1 + ps1;
@@ -271,8 +308,8 @@ __global__ void __launch_bounds__(NT) flash_fwd_kernel(const Params p) {
       o[nb][3] *= c1;
     }
     mma_p_t(o, s, sV + buf * TILE_BYTES, lane);
-    __syncthreads();
   }
+  __syncthreads();   // the K buffers double as the output staging tile
   l0 = quad_sum(l0);
   l1 = quad_sum(l1);
   const float i0 = l0 > 0.f ? 1.0f / l0 : 0.f, i1 = l1 > 0.f ? 1.0f / l1 : 0.f;
@@ -288,16 +325,16 @@ __global__ void __launch_bounds__(NT) flash_fwd_kernel(const Params p) {
     if (r0 < p.nq) lse[r0] = l0 > 0.f ? m0 + log2f(l0) : INFINITY;
     if (r0 + 8 < p.nq) lse[r0 + 8] = l1 > 0.f ? m1 + log2f(l1) : INFINITY;
   }
-  // sQ is free (Q lives in registers since the first tile; the loop's last barrier ordered every warp's reads)
-  store_rows(sQ, smem, o, warp * 16, lane, p.out + b * p.o_bs + (int64_t)q0 * p.ldo + h * DH, p.ldo, p.nq - q0);
+  store_rows(sK, smem, o, warp * 16, lane, p.out + b * p.o_bs + (int64_t)q0 * p.ldo + h * DH, p.ldo, p.nq - q0);
 }
 
 // ------------------------------------------------------------------------------------------------ backward A: dQ
-__global__ void __launch_bounds__(NT) flash_bwd_dq_kernel(const Params p) {
-  __shared__ __align__(128) uint8_t smem[6 * TILE_BYTES];
+__global__ void __launch_bounds__(NT, 3) flash_bwd_dq_kernel(const Params p) {
+  __shared__ __align__(128) uint8_t smem[4 * TILE_BYTES];
+  __shared__ __align__(16) float s_km[2][BN];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gq = lane >> 2, t = lane & 3;
   const int q0 = blockIdx.x * BM, h = blockIdx.y, b = blockIdx.z;
-  const uint32_t sQ = smem_u32(smem), sdO = sQ + TILE_BYTES, sK = sQ + 2 * TILE_BYTES, sV = sQ + 4 * TILE_BYTES;
+  const uint32_t sK = smem_u32(smem), sV = sK + 2 * TILE_BYTES, sQ = sK + TILE_BYTES, sdO = sV + TILE_BYTES;
   pdl_wait();
   pdl_trigger();
   const bf16* kg = p.k + b * p.k_bs + h * DH;
@@ -305,39 +342,40 @@ __global__ void __launch_bounds__(NT) flash_bwd_dq_kernel(const Params p) {
   const bf16* dog = p.dout + b * p.do_bs + (int64_t)q0 * p.lddo + h * DH;
   const bf16* og = p.o + b * p.o_bs + (int64_t)q0 * p.ldo + h * DH;
   const int ntile = (p.nk + BN - 1) / BN;
-  load_tile(sQ, p.q + b * p.q_bs + (int64_t)q0 * p.ldq + h * DH, p.ldq, p.nq - q0, tid);
+  const bool active = q0 + warp * 16 < p.nq;
+  load_tile(sQ, p.q + b * p.q_bs + (int64_t)q0 * p.ldq + h * DH, p.ldq, p.nq - q0, tid);   // staged in the 2nd buffers
   load_tile(sdO, dog, p.lddo, p.nq - q0, tid);
   load_tile(sK, kg, p.ldk, p.nk, tid);
   load_tile(sV, vg, p.ldv, p.nk, tid);
+  stage_kmask(s_km[0], p, b, 0, tid);
   cp_async_commit();
 
   const int r0 = q0 + warp * 16 + gq;
-  const int64_t rng0 = (((int64_t)b * p.H + h) * p.nq + r0) * p.nk, rng1 = rng0 + 8 * (int64_t)p.nk;
+  const uint32_t t16 = p.thresh >> 16;
+  const uint32_t rh0 = row_hash(p.seed, ((int64_t)b * p.H + h) * p.nq + r0), rh1 = row_hash(p.seed, ((int64_t)b * p.H + h) * p.nq + r0 + 8);
   // D = rowsum(dO * O) for rows r0, r0+8: the quad's 4 lanes take 16 columns each
   float d0 = 0.f, d1 = 0.f;
-  {
 #pragma unroll
-    for (int rr = 0; rr < 2; ++rr) {
-      const int r = r0 + rr * 8;
-      float acc = 0.f;
-      if (r < p.nq) {
-        const int lr = r - q0;
+  for (int rr = 0; rr < 2; ++rr) {
+    const int r = r0 + rr * 8;
+    float acc = 0.f;
+    if (r < p.nq) {
+      const int lr = r - q0;
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          const uint4 a = *reinterpret_cast<const uint4*>(dog + (int64_t)lr * p.lddo + t * 16 + c * 8);
-          const uint4 o4 = *reinterpret_cast<const uint4*>(og + (int64_t)lr * p.ldo + t * 16 + c * 8);
-          const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&a);
-          const __nv_bfloat162* po = reinterpret_cast<const __nv_bfloat162*>(&o4);
+      for (int c = 0; c < 2; ++c) {
+        const uint4 a = *reinterpret_cast<const uint4*>(dog + (int64_t)lr * p.lddo + t * 16 + c * 8);
+        const uint4 o4 = *reinterpret_cast<const uint4*>(og + (int64_t)lr * p.ldo + t * 16 + c * 8);
+        const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&a);
+        const __nv_bfloat162* po = reinterpret_cast<const __nv_bfloat162*>(&o4);
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float2 fa = __bfloat1622float2(pa[e]), fo = __bfloat1622float2(po[e]);
-            acc += fa.x * fo.x + fa.y * fo.y;
-          }
+        for (int e = 0; e < 4; ++e) {
+          const float2 fa = __bfloat1622float2(pa[e]), fo = __bfloat1622float2(po[e]);
+          acc += fa.x * fo.x + fa.y * fo.y;
         }
       }
-      acc = quad_sum(acc);
-      if (rr == 0) d0 = acc; else d1 = acc;
     }
+    acc = quad_sum(acc);
+    if (rr == 0) d0 = acc; else d1 = acc;
   }
   const float* lseg = p.lse + ((int64_t)b * p.H + h) * p.nq;
   const float lse0 = r0 < p.nq ? lseg[r0] : INFINITY, lse1 = r0 + 8 < p.nq ? lseg[r0 + 8] : INFINITY;
@@ -346,27 +384,27 @@ __global__ void __launch_bounds__(NT) flash_bwd_dq_kernel(const Params p) {
     if (r0 < p.nq) ds[r0] = d0;
     if (r0 + 8 < p.nq) ds[r0 + 8] = d1;
   }
-  float* db0 = (p.dbias && r0 < p.nq) ? p.dbias + ((int64_t)b * p.nq + r0) * p.nk : nullptr;
-  float* db1 = (p.dbias && r0 + 8 < p.nq) ? p.dbias + ((int64_t)b * p.nq + r0 + 8) * p.nk : nullptr;
 
   float dq[8][4];
 #pragma unroll
   for (int i = 0; i < 8; ++i) dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f;
   uint32_t qf[4][4], dof[4][4];
+  cp_async_wait<0>();
+  __syncthreads();
+  load_a_frags(sQ, warp * 16, lane, qf);
+  load_a_frags(sdO, warp * 16, lane, dof);
 
   for (int j = 0; j < ntile; ++j) {
     const int buf = j & 1;
+    cp_async_wait<0>();
+    __syncthreads();
     if (j + 1 < ntile) {
       load_tile(sK + (buf ^ 1) * TILE_BYTES, kg + (int64_t)(j + 1) * BN * p.ldk, p.ldk, p.nk - (j + 1) * BN, tid);
       load_tile(sV + (buf ^ 1) * TILE_BYTES, vg + (int64_t)(j + 1) * BN * p.ldv, p.ldv, p.nk - (j + 1) * BN, tid);
+      stage_kmask(s_km[buf ^ 1], p, b, j + 1, tid);
+      cp_async_commit();
     }
-    cp_async_commit();
-    cp_async_wait<1>();
-    __syncthreads();
-    if (j == 0) {
-      load_a_frags(sQ, warp * 16, lane, qf);
-      load_a_frags(sdO, warp * 16, lane, dof);
-    }
+    if (!active) continue;
     float s[8][4], dp[8][4];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -374,38 +412,57 @@ __global__ void __launch_bounds__(NT) flash_bwd_dq_kernel(const Params p) {
       dp[i][0] = dp[i][1] = dp[i][2] = dp[i][3] = 0.f;
     }
     mma_a_tT(s, qf, sK + buf * TILE_BYTES, lane);
-    logits_qk(s, p, b, r0, j, t);
+    logits_qk(s, p, s_km[buf], b, r0, j, t);
     mma_a_tT(dp, dof, sV + buf * TILE_BYTES, lane);
 #pragma unroll
     for (int nb = 0; nb < 8; ++nb) {
+      float g00 = dp[nb][0], g01 = dp[nb][1], g10 = dp[nb][2], g11 = dp[nb][3];
+      if (p.thresh) {
+        const uint32_t pair = j * (BN / 2) + nb * 4 + t;
+        const uint32_t x0 = mix_pair(rh0, pair), x1 = mix_pair(rh1, pair);
+        g00 = (x0 & 0xFFFFu) >= t16 ? g00 * p.scale : 0.f;
+        g01 = (x0 >> 16) >= t16 ? g01 * p.scale : 0.f;
+        g10 = (x1 & 0xFFFFu) >= t16 ? g10 * p.scale : 0.f;
+        g11 = (x1 >> 16) >= t16 ? g11 * p.scale : 0.f;
+      }
+      s[nb][0] = ex2(s[nb][0] - lse0) * (g00 - d0);   // -inf logits / +inf lse -> p = 0
+      s[nb][1] = ex2(s[nb][1] - lse0) * (g01 - d0);
+      s[nb][2] = ex2(s[nb][2] - lse1) * (g10 - d1);
+      s[nb][3] = ex2(s[nb][3] - lse1) * (g11 - d1);
+    }
+    if (p.dbias) {   // graph-bias gradient (global map encoder): sum over heads with fp32 atomics
+      float* db0 = r0 < p.nq ? p.dbias + ((int64_t)b * p.nq + r0) * p.nk : nullptr;
+      float* db1 = r0 + 8 < p.nq ? p.dbias + ((int64_t)b * p.nq + r0 + 8) * p.nk : nullptr;
 #pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int col = j * BN + nb * 8 + 2 * t + e;
-        const float p0 = ex2(s[nb][e] - lse0), p1 = ex2(s[nb][2 + e] - lse1);   // -inf logits / +inf lse -> 0
-        float g0 = dp[nb][e], g1 = dp[nb][2 + e];
-        if (p.thresh) {
-          g0 = drop_keep(p.seed, rng0 + col, p.thresh) ? g0 * p.scale : 0.f;
-          g1 = drop_keep(p.seed, rng1 + col, p.thresh) ? g1 * p.scale : 0.f;
+      for (int nb = 0; nb < 8; ++nb) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int col = j * BN + nb * 8 + 2 * t + e;
+          if (col < p.nk) {
+            if (db0) atomicAdd(db0 + col, s[nb][e]);
+            if (db1) atomicAdd(db1 + col, s[nb][2 + e]);
+          }
         }
-        const float ds0 = p0 * (g0 - d0), ds1 = p1 * (g1 - d1);
-        if (col < p.nk) {
-          if (db0) atomicAdd(db0 + col, ds0);
-          if (db1) atomicAdd(db1 + col, ds1);
-        }
-        s[nb][e] = ds0 * p.alpha;
-        s[nb][2 + e] = ds1 * p.alpha;
       }
     }
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) {
+      s[nb][0] *= p.alpha;
+      s[nb][1] *= p.alpha;
+      s[nb][2] *= p.alpha;
+      s[nb][3] *= p.alpha;
+    }
     mma_p_t(dq, s, sK + buf * TILE_BYTES, lane);
-    __syncthreads();
   }
-  store_rows(sQ, smem, dq, warp * 16, lane, p.dq + b * p.dq_bs + (int64_t)q0 * p.lddq + h * DH, p.lddq, p.nq - q0);
+  __syncthreads();
+  store_rows(sK, smem, dq, warp * 16, lane, p.dq + b * p.dq_bs + (int64_t)q0 * p.lddq + h * DH, p.lddq, p.nq - q0);
 }
 
 // ------------------------------------------------------------------------------------------------ backward B: dK, dV
 __global__ void __launch_bounds__(NT) flash_bwd_dkv_kernel(const Params p) {
   __shared__ __align__(128) uint8_t smem[4 * TILE_BYTES];
   __shared__ float s_lse[2][BN], s_dsum[2][BN];
+  __shared__ uint32_t s_rh[2][BN];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gq = lane >> 2, t = lane & 3;
   const int k0 = blockIdx.x * BM, h = blockIdx.y, b = blockIdx.z;
   const uint32_t sQ = smem_u32(smem), sdO = sQ + 2 * TILE_BYTES;
@@ -423,9 +480,11 @@ __global__ void __launch_bounds__(NT) flash_bwd_dkv_kernel(const Params p) {
   cp_async_commit();
   load_tile(sQ, qg, p.ldq, p.nq, tid);
   load_tile(sdO, dog, p.lddo, p.nq, tid);
+  const int64_t rngb = ((int64_t)b * p.H + h) * p.nq;
   if (tid < BN) {
     s_lse[0][tid] = tid < p.nq ? lseg[tid] : INFINITY;
     s_dsum[0][tid] = tid < p.nq ? dsg[tid] : 0.f;
+    if (p.thresh) s_rh[0][tid] = row_hash(p.seed, rngb + tid);
   }
   cp_async_commit();
   cp_async_wait<1>();
@@ -433,12 +492,12 @@ __global__ void __launch_bounds__(NT) flash_bwd_dkv_kernel(const Params p) {
   uint32_t kf[4][4], vf[4][4];
   load_a_frags(sQ + TILE_BYTES, warp * 16, lane, kf);
   load_a_frags(sdO + TILE_BYTES, warp * 16, lane, vf);
-  __syncthreads();   // everyone has its K / V fragments before tile 1 overwrites the staging halves
+  const bool active = k0 + warp * 16 < p.nk;
 
   const int kr0 = k0 + warp * 16 + gq;   // this thread's keys: kr0 and kr0 + 8
   const float km0 = (kr0 < p.nk) ? (p.kmask ? p.kmask[(int64_t)b * p.nk + kr0] : 0.f) : -INFINITY;
   const float km1 = (kr0 + 8 < p.nk) ? (p.kmask ? p.kmask[(int64_t)b * p.nk + kr0 + 8] : 0.f) : -INFINITY;
-  const int64_t rngb = ((int64_t)b * p.H + h) * p.nq;
+  const uint32_t t16 = p.thresh >> 16, pair0 = (uint32_t)kr0 >> 1, sh = (kr0 & 1) * 16;
   float dk[8][4], dv[8][4];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
@@ -448,6 +507,8 @@ __global__ void __launch_bounds__(NT) flash_bwd_dkv_kernel(const Params p) {
 
   for (int j = 0; j < ntile; ++j) {
     const int buf = j & 1;
+    cp_async_wait<0>();
+    __syncthreads();   // tile j landed; all warps hold their K / V fragments and are done with tile j-1
     if (j + 1 < ntile) {
       const int qn = (j + 1) * BN;
       load_tile(sQ + (buf ^ 1) * TILE_BYTES, qg + (int64_t)qn * p.ldq, p.ldq, p.nq - qn, tid);
@@ -455,11 +516,11 @@ __global__ void __launch_bounds__(NT) flash_bwd_dkv_kernel(const Params p) {
       if (tid < BN) {
         s_lse[buf ^ 1][tid] = qn + tid < p.nq ? lseg[qn + tid] : INFINITY;
         s_dsum[buf ^ 1][tid] = qn + tid < p.nq ? dsg[qn + tid] : 0.f;
+        if (p.thresh) s_rh[buf ^ 1][tid] = row_hash(p.seed, rngb + qn + tid);
       }
+      cp_async_commit();
     }
-    cp_async_commit();
-    cp_async_wait<1>();
-    __syncthreads();
+    if (!active) continue;
 
     // S^T (keys x queries) and dP^T
     float s[8][4], dp[8][4];
@@ -487,8 +548,9 @@ __global__ void __launch_bounds__(NT) flash_bwd_dkv_kernel(const Params p) {
         const float p1 = ex2((s[nb][2 + e] * p.alpha + km1 + b1) * LOG2E - lse);
         float g0 = dp[nb][e], g1 = dp[nb][2 + e], q0v = p0, q1v = p1;
         if (p.thresh) {
-          const int64_t base = (rngb + qi) * p.nk;
-          const bool keep0 = drop_keep(p.seed, base + kr0, p.thresh), keep1 = drop_keep(p.seed, base + kr0 + 8, p.thresh);
+          const uint32_t rh = s_rh[buf][ql];
+          const bool keep0 = ((mix_pair(rh, pair0) >> sh) & 0xFFFFu) >= t16;
+          const bool keep1 = ((mix_pair(rh, pair0 + 4) >> sh) & 0xFFFFu) >= t16;
           g0 = keep0 ? g0 * p.scale : 0.f;
           g1 = keep1 ? g1 * p.scale : 0.f;
           q0v = keep0 ? p0 * p.scale : 0.f;
@@ -502,8 +564,8 @@ __global__ void __launch_bounds__(NT) flash_bwd_dkv_kernel(const Params p) {
     }
     mma_p_t(dv, pd, sdO + buf * TILE_BYTES, lane);
     mma_p_t(dk, s, sQ + buf * TILE_BYTES, lane);
-    __syncthreads();
   }
+  __syncthreads();
   store_rows(sQ, smem, dk, warp * 16, lane, p.dk + b * p.dk_bs + (int64_t)k0 * p.lddk + h * DH, p.lddk, p.nk - k0);
   store_rows(sdO, smem + 2 * TILE_BYTES, dv, warp * 16, lane, p.dv + b * p.dv_bs + (int64_t)k0 * p.lddv + h * DH, p.lddv,
              p.nk - k0);
