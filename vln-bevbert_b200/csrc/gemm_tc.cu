@@ -74,13 +74,20 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmKParams& p, int tile)
 
 __device__ __forceinline__ float bf2f(__nv_bfloat16 v) { return __bfloat162float(v); }
 
+// CTAS = 1: one CTA per 128 x block_n tile.  CTAS = 2: a CTA pair (cluster of 2 on one TPC) per 256 x block_n tile with
+// tcgen05.mma.cta_group::2 -- each CTA stages its 128 rows of A and half of the B tile, the leader issues the MMAs,
+// every CTA runs the epilogue of its own 128 accumulator rows.
+template <int CTAS>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const GemmKParams p, int total_tiles) {
   extern __shared__ uint8_t smem_raw[];
-  // 1024-byte alignment for SWIZZLE_128B atoms
+  // 1024-byte alignment for SWIZZLE_128B atoms (the dynamic smem base offset is the same in both CTAs of a pair)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int b_stage_bytes = p.block_n * BLOCK_K * 2;
+  const int rank = CTAS == 2 ? (int)cluster_ctarank() : 0;
+  const int tile0 = blockIdx.x / CTAS, tile_step = gridDim.x / CTAS;
+  const int bn_local = p.block_n / CTAS;                 // B rows staged by this CTA
+  const int b_stage_bytes = bn_local * BLOCK_K * 2;
   const int stage_bytes = A_STAGE_BYTES + b_stage_bytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.stages * stage_bytes);
   uint64_t* empty_bar = full_bar + MAX_STAGES;
@@ -103,16 +110,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 8);
+      mbar_init(&tmem_empty[i], 8 * CTAS);   // the leader's MMA thread waits for the epilogue warps of both CTAs
     }
     fence_mbar_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_ptr_smem, TMEM_COLS);
-    tmem_relinquish();
+    if (CTAS == 2) {
+      tmem_alloc_2sm(tmem_ptr_smem, TMEM_COLS);
+      tmem_relinquish_2sm();
+    } else {
+      tmem_alloc(tmem_ptr_smem, TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CTAS == 2) cluster_sync_all();   // the peer's barriers must exist before TMA / commits signal them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   // Everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the previous kernel's tail;
@@ -125,29 +138,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      auto load = [&](void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3) {
+        if (CTAS == 2) tma_load_4d_2sm(dst, m, bar, c0, c1, c2, c3);   // completes on the LEADER's barrier
+        else tma_load_4d(dst, m, bar, c0, c1, c2, c3);
+      };
+      for (int tile = tile0; tile < total_tiles; tile += tile_step) {
         const TileCoord t = decode_tile(p, tile);
         const int kb0 = t.split * p.kb_per_split;
         const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
-        const int m0 = t.m_tile * BLOCK_M;
-        const int n0 = t.n_tile * p.block_n;
+        const int m0 = (t.m_tile * CTAS + rank) * BLOCK_M;
+        const int n0 = t.n_tile * p.block_n + rank * bn_local;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * stage_bytes;
           uint8_t* sb = sa + A_STAGE_BYTES;
-          mbar_expect_tx(&full_bar[stage], stage_bytes);
+          if (rank == 0) mbar_expect_tx(&full_bar[stage], stage_bytes * CTAS);
           const int k0 = kb * BLOCK_K;
           if (!p.a_mn) {
-            tma_load_4d(sa, &tmap_a, &full_bar[stage], k0, m0, t.b1, t.b2);
+            load(sa, &tmap_a, &full_bar[stage], k0, m0, t.b1, t.b2);
           } else {
-            tma_load_4d(sa, &tmap_a, &full_bar[stage], m0, k0, t.b1, t.b2);
-            tma_load_4d(sa + 8192, &tmap_a, &full_bar[stage], m0 + 64, k0, t.b1, t.b2);
+            load(sa, &tmap_a, &full_bar[stage], m0, k0, t.b1, t.b2);
+            load(sa + 8192, &tmap_a, &full_bar[stage], m0 + 64, k0, t.b1, t.b2);
           }
           if (!p.b_mn) {
-            tma_load_4d(sb, &tmap_b, &full_bar[stage], k0, n0, t.b1, t.b2);
+            load(sb, &tmap_b, &full_bar[stage], k0, n0, t.b1, t.b2);
           } else {
-            for (int j = 0; j < p.block_n / 64; ++j)
-              tma_load_4d(sb + j * 8192, &tmap_b, &full_bar[stage], n0 + 64 * j, k0, t.b1, t.b2);
+            for (int j = 0; j < bn_local / 64; ++j)
+              load(sb + j * 8192, &tmap_b, &full_bar[stage], n0 + 64 * j, k0, t.b1, t.b2);
           }
           if (++stage == p.stages) {
             stage = 0;
@@ -158,13 +175,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(BLOCK_M, p.block_n, p.a_mn, p.b_mn);
+    if (lane == 0 && rank == 0) {
+      const uint32_t idesc = umma_idesc_bf16(BLOCK_M * CTAS, p.block_n, p.a_mn, p.b_mn);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < total_tiles; tile += tile_step) {
         const TileCoord t = decode_tile(p, tile);
         const int kb0 = t.split * p.kb_per_split;
         const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
@@ -182,15 +199,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                                        : umma_smem_desc(sa + k * 32, 16, 1024);
             const uint64_t db = p.b_mn ? umma_smem_desc(sb + k * 2048, 8192, 1024)
                                        : umma_smem_desc(sb + k * 32, 16, 1024);
-            umma_bf16_ss(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if (CTAS == 2) umma_bf16_ss_2sm(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            else umma_bf16_ss(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+          // smem slot reusable once these MMAs retire (in both CTAs of a pair)
+          if (CTAS == 2) umma_commit_2sm(&empty_bar[stage]);
+          else umma_commit(&empty_bar[stage]);
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+        // accumulator complete -> epilogue (of both CTAs)
+        if (CTAS == 2) umma_commit_2sm(&tmem_full[acc]);
+        else umma_commit(&tmem_full[acc]);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
@@ -206,9 +228,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     uint32_t acc_phase = 0;
     const bool need_aux = p.epi_mul != 0;
     const bool need_add = p.add_in != nullptr;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int tile = tile0; tile < total_tiles; tile += tile_step) {
       const TileCoord t = decode_tile(p, tile);
-      const int row = t.m_tile * BLOCK_M + quarter * 32 + lane;
+      const int row = (t.m_tile * CTAS + rank) * BLOCK_M + quarter * 32 + lane;
       const int n0 = t.n_tile * p.block_n;
       const bool row_ok = row < p.M;
       const long long row_off = (long long)t.b1 * p.d_s1 + (long long)t.b2 * p.d_s2 + (long long)row * p.ldd;
@@ -362,17 +384,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (lane == 0) {
+        if (CTAS == 2) mbar_arrive_leader(&tmem_empty[acc]);
+        else mbar_arrive(&tmem_empty[acc]);
+      }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CTAS == 2) cluster_sync_all();   // the leader's MMAs read the peer's smem and write its TMEM until the very end
+  else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if (CTAS == 2) tmem_dealloc_2sm(tmem_base, TMEM_COLS);
+    else tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
@@ -443,9 +470,45 @@ static int init_device_info() {
   if (cudaGetDevice(&dev) != cudaSuccess) return set_error("cudaGetDevice failed");
   cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
   cudaDeviceGetAttribute(&g_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-  if (cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin) != cudaSuccess)
+  if (cudaFuncSetAttribute(gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin) != cudaSuccess ||
+      cudaFuncSetAttribute(gemm_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin) != cudaSuccess)
     return set_error("cudaFuncSetAttribute(max dynamic smem) failed for gemm_tc_kernel");
   return 0;
+}
+
+// number of CTA pairs that can be resident at once (GPCs with an odd SM count leave an SM without a partner)
+static int max_pairs() {
+  static int v = -1;
+  if (v < 0) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(g_num_sms / 2 * 2);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = g_smem_optin;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, gemm_tc_kernel<2>, &cfg) != cudaSuccess || n <= 0) {
+      cudaGetLastError();
+      n = g_num_sms / 2;
+    }
+    v = n < g_num_sms / 2 ? n : g_num_sms / 2;
+  }
+  return v;
+}
+
+// BB_GEMM_2CTA: 0 = single-CTA tiles only, 1 (default) = CTA pairs wherever the shape allows
+static int two_cta_mode() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("BB_GEMM_2CTA");
+    v = e ? atoi(e) : 1;
+  }
+  return v;
 }
 
 }  // namespace bb
@@ -472,7 +535,9 @@ extern "C" int bb_gemm_bf16(const bb_gemm_args* a, void* stream_) {
   p.nb2 = nb2;
   p.a_mn = a->a_mn ? 1 : 0;
   p.b_mn = a->b_mn ? 1 : 0;
-  p.m_tiles = (a->M + BLOCK_M - 1) / BLOCK_M;
+  // CTA pairs (256-row tiles) unless the problem has a single 128-row tile; block_n legality is checked below
+  int ctas = (two_cta_mode() && a->M > BLOCK_M) ? 2 : 1;
+  p.m_tiles = (a->M + BLOCK_M * ctas - 1) / (BLOCK_M * ctas);
   // N tile
   int bn = a->block_n;
   if (bn <= 0) {
@@ -484,13 +549,18 @@ extern "C" int bb_gemm_bf16(const bb_gemm_args* a, void* stream_) {
       // launch is ~ rounds x k-blocks x t(bn) with t(256) ~ 1.3 t(128): pick the width with fewer weighted rounds.
       const long long per = (long long)p.m_tiles * nb1 * nb2 * split_k_req;
       const int n256 = (a->N + 255) / 256, n128 = (a->N + 127) / 128;
-      const long long r256 = (per * n256 + g_num_sms - 1) / g_num_sms, r128 = (per * n128 + g_num_sms - 1) / g_num_sms;
+      const int units = ctas == 2 ? max_pairs() : g_num_sms;
+      const long long r256 = (per * n256 + units - 1) / units, r128 = (per * n128 + units - 1) / units;
       bn = (13 * r256 <= 10 * r128) ? 256 : 128;
       if (a->N <= 256 && bn == 256) bn = ((a->N + gran - 1) / gran) * gran;
     }
   }
   if (bn < 16 || bn > 256 || bn % 16 != 0 || (p.b_mn && bn % 64 != 0))
     return set_error("bb_gemm_bf16: invalid block_n");
+  if (ctas == 2 && (bn % 32 != 0 || (p.b_mn && bn % 128 != 0))) {   // each CTA stages bn/2 rows of B
+    ctas = 1;
+    p.m_tiles = (a->M + BLOCK_M - 1) / BLOCK_M;
+  }
   p.block_n = bn;
   p.n_tiles = (a->N + bn - 1) / bn;
   p.kb_total = (a->K + BLOCK_K - 1) / BLOCK_K;
@@ -526,7 +596,7 @@ extern "C" int bb_gemm_bf16(const bb_gemm_args* a, void* stream_) {
     p.vec_ok = ok ? 1 : 0;
   }
 
-  const int stage_bytes = A_STAGE_BYTES + bn * BLOCK_K * 2;
+  const int stage_bytes = A_STAGE_BYTES + (bn / ctas) * BLOCK_K * 2;
   int stages = (g_smem_optin - 1024 - 512 - 2048) / stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   {
@@ -546,13 +616,14 @@ extern "C" int bb_gemm_bf16(const bb_gemm_args* a, void* stream_) {
   if (!p.a_mn) e = make_map(&ta, a->A, a->K, a->M, nb1, nb2, a->lda, a->a_s1, a->a_s2, BLOCK_M);
   else e = make_map(&ta, a->A, a->M, a->K, nb1, nb2, a->lda, a->a_s1, a->a_s2, BLOCK_K);
   if (e) return e;
-  if (!p.b_mn) e = make_map(&tb, a->B, a->K, a->N, nb1, nb2, a->ldb, a->b_s1, a->b_s2, bn);
+  if (!p.b_mn) e = make_map(&tb, a->B, a->K, a->N, nb1, nb2, a->ldb, a->b_s1, a->b_s2, bn / ctas);
   else e = make_map(&tb, a->B, a->N, a->K, nb1, nb2, a->ldb, a->b_s1, a->b_s2, BLOCK_K);
   if (e) return e;
 
   const long long total = (long long)p.m_tiles * p.n_tiles * nb1 * nb2 * p.split_k;
   if (total > 0x7fffffffLL) return set_error("bb_gemm_bf16: too many tiles");
-  const int grid = total < g_num_sms ? (int)total : g_num_sms;
+  const int units = ctas == 2 ? max_pairs() : g_num_sms;
+  const int grid = (total < units ? (int)total : units) * ctas;
   ProfRec* rec = nullptr;
   if (g_prof_on) {
     if (g_prof_used == g_prof.size()) {
@@ -566,7 +637,8 @@ extern "C" int bb_gemm_bf16(const bb_gemm_args* a, void* stream_) {
     rec->dims[4] = p.a_mn; rec->dims[5] = p.b_mn;
     cudaEventRecord(rec->e0, stream);
   }
-  bb::launch_pdl(gemm_tc_kernel, grid, NUM_THREADS, smem_bytes, stream, ta, tb, p, (int)total);
+  if (ctas == 2) bb::launch_pdl_cluster(gemm_tc_kernel<2>, grid, NUM_THREADS, smem_bytes, stream, 2, ta, tb, p, (int)total);
+  else bb::launch_pdl(gemm_tc_kernel<1>, grid, NUM_THREADS, smem_bytes, stream, ta, tb, p, (int)total);
   if (rec) cudaEventRecord(rec->e1, stream);
   count_launch();
   return check_launch("gemm_tc_kernel");
