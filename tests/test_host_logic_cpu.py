@@ -76,3 +76,24 @@ def test_step_arena_gives_identical_gradients(emu):
         grads.append({n: p.grad for n, p in model.named_parameters() if p.grad is not None})
     for n, g in grads[0].items():
         assert torch.equal(g, grads[1][n]) and torch.equal(g, grads[2][n]), n
+
+
+def test_direct_param_grads_equal_autograd_accumulation(emu):
+    """parallel.direct_param_grads(): blocks write p.grad themselves; same gradients (shared word embeddings
+    accumulate), also over two accumulated backward passes."""
+    from bevbert_b200 import parallel
+    cfg, scfg = small_config(), small_synth()
+    b = synth.make_batch(scfg, seed=13, task="mlm")
+    grads = {}
+    for mode in (False, True):
+        parallel.direct_param_grads(mode)
+        try:
+            model = synth.det_init_(GlocalTextPathCMTPreTraining(cfg), seed=3).train()
+            for _ in range(2):
+                model(synth.clone_batch(b), "mlm").mean().backward()
+            grads[mode] = {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None}
+        finally:
+            parallel.direct_param_grads(False)
+    assert set(grads[False]) == set(grads[True])
+    for n, g in grads[False].items():
+        assert torch.allclose(g, grads[True][n], rtol=1e-6, atol=1e-7), n

@@ -964,6 +964,9 @@ def to_f32(x):
 
 
 # =============================================================================================== autograd glue
+DIRECT_PARAM_GRADS = False   # parallel.direct_param_grads(): blocks assign p.grad themselves
+
+
 class _BlockFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, impl, n_in, *args):
@@ -981,6 +984,19 @@ class _BlockFn(torch.autograd.Function):
         ctx.st = None
         gin = list(gin) + [None] * (ctx.n_in - len(gin))
         needs = ctx.needs_input_grad[2:]
+        if DIRECT_PARAM_GRADS:
+            # hand the parameter gradients over without one AccumulateGrad node per parameter (see parallel.py)
+            n_in = ctx.n_in
+            for i, (p, g) in enumerate(zip(ctx.params, gpar)):
+                if g is not None and needs[n_in + i]:
+                    if not g.is_contiguous():          # sliced views of padded operands (tiny K): as AccumulateGrad does
+                        g = g.contiguous()
+                    if p.grad is None:
+                        p.grad = g
+                    else:
+                        p.grad.add_(g)
+            full = [g if n else None for g, n in zip(gin, needs)] + [None] * len(ctx.params)
+            return (None, None, *full)
         full = list(gin) + list(gpar)
         full = [g if n else None for g, n in zip(full, needs)]
         return (None, None, *full)

@@ -266,20 +266,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + acc * 256;
-      for (int c = half * 16; c < p.block_n; c += 32) {
+      // One 16-column chunk: r holds its accumulators (already waited for).  The TMEM load of the NEXT chunk is issued
+      // before this runs, so the tcgen05.ld round trip overlaps the arithmetic and stores of the current chunk.
+      auto process = [&](const int c, uint32_t (&r)[16], const uint4 (&qa)[2], const uint4 (&qd)[2]) {
         const int col0 = n0 + c;
-        if (col0 >= p.N) break;  // warp-uniform
-        uint32_t r[16];
-        tmem_ld16(taddr + c, r);
-        // operands of this chunk (prefetched) -> locals, then start fetching the next chunk's
         __align__(16) __nv_bfloat16 ha[16], hd[16];
-        reinterpret_cast<uint4*>(ha)[0] = pa[0];
-        reinterpret_cast<uint4*>(ha)[1] = pa[1];
-        reinterpret_cast<uint4*>(hd)[0] = pd[0];
-        reinterpret_cast<uint4*>(hd)[1] = pd[1];
-        prefetch(c + 32);
-        tmem_ld_wait();
-        if (!row_ok) continue;
+        reinterpret_cast<uint4*>(ha)[0] = qa[0];
+        reinterpret_cast<uint4*>(ha)[1] = qa[1];
+        reinterpret_cast<uint4*>(hd)[0] = qd[0];
+        reinterpret_cast<uint4*>(hd)[1] = qd[1];
+        if (!row_ok) return;
         float v[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) * p.alpha;
@@ -381,6 +377,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               if (col0 + i < p.N) D[i] = __float2bfloat16(v[i]);
           }
         }
+            };
+      auto valid = [&](int c) { return c < p.block_n && n0 + c < p.N; };   // warp-uniform
+      uint32_t ra[16], rb[16];
+      int c = half * 16;
+      if (valid(c)) tmem_ld16(taddr + c, ra);
+      while (valid(c)) {
+        uint4 qa[2] = {pa[0], pa[1]}, qd[2] = {pd[0], pd[1]};
+        prefetch(c + 32);
+        tmem_ld_wait_regs(ra);
+        const bool nb = valid(c + 32);
+        if (nb) tmem_ld16(taddr + c + 32, rb);
+        process(c, ra, qa, qd);
+        if (!nb) break;
+        c += 32;
+        uint4 qa2[2] = {pa[0], pa[1]}, qd2[2] = {pd[0], pd[1]};
+        prefetch(c + 32);
+        tmem_ld_wait_regs(rb);
+        if (valid(c + 32)) tmem_ld16(taddr + c + 32, ra);
+        process(c, rb, qa2, qd2);
+        c += 32;
       }
       tc_fence_before();
       __syncwarp();
@@ -535,8 +551,14 @@ extern "C" int bb_gemm_bf16(const bb_gemm_args* a, void* stream_) {
   p.nb2 = nb2;
   p.a_mn = a->a_mn ? 1 : 0;
   p.b_mn = a->b_mn ? 1 : 0;
-  // CTA pairs (256-row tiles) unless the problem has a single 128-row tile; block_n legality is checked below
-  int ctas = (two_cta_mode() && a->M > BLOCK_M) ? 2 : 1;
+  // CTA pairs (256-row tiles, +7..11 % on machine-filling problems) only when the single-CTA tiling would need at
+  // least two full rounds of the machine: a pair costs a cluster launch plus two cluster barriers, which the 10-30 us
+  // language-encoder products do not amortise (measured).  BB_GEMM_2CTA=2 forces pairs wherever legal (tests).
+  int ctas = 1;
+  if (two_cta_mode() && a->M > BLOCK_M) {
+    const long long t1 = (long long)((a->M + BLOCK_M - 1) / BLOCK_M) * ((a->N + 255) / 256) * nb1 * nb2 * split_k_req;
+    if (two_cta_mode() >= 2 || t1 >= 2LL * g_num_sms) ctas = 2;
+  }
   p.m_tiles = (a->M + BLOCK_M * ctas - 1) / (BLOCK_M * ctas);
   // N tile
   int bn = a->block_n;

@@ -95,6 +95,7 @@ class PreparedList(list):
     """A host id list that carries index tensors precomputed from it (see prepare_batch)."""
     host_segments = None
     host_fusion = None
+    host_mlm = None
 
 
 def prepare_batch(batch):
@@ -113,6 +114,14 @@ def prepare_batch(batch):
         Kc = batch["bev_cand_idxs"].shape[1]
         E2 = _fusion_matches(gv, [c[-1] for c in batch["traj_cand_vpids"]], G, Kc)
         gv.host_fusion = ((G, Kc), E2.pin_memory() if pin else E2)
+    lab = batch.get("txt_labels")
+    if torch.is_tensor(lab) and not lab.is_cuda:
+        # masked-token rows and their labels (pretrain_cmt.py:259-270 selects them with a boolean mask on the device,
+        # which costs a device->host sync per MLM step); the masking was drawn on the host, so the list is known here
+        flat = lab.reshape(-1)
+        idx = torch.nonzero(flat != -1, as_tuple=False).reshape(-1)
+        sel = flat[idx].contiguous()
+        gv.host_mlm = (tuple(lab.shape), idx.pin_memory() if pin else idx, sel.pin_memory() if pin else sel)
     out = dict(batch)
     out["gmap_vpids"] = gv
     return out

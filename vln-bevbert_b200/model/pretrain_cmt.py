@@ -160,9 +160,15 @@ class GlocalTextPathCMTPreTraining(PreTrainedBase):
             txt_ids, txt_lens, traj_view_img_fts, traj_obj_img_fts, traj_loc_fts, traj_nav_types, traj_step_lens,
             traj_vp_view_lens, traj_vp_obj_lens, traj_vpids, traj_cand_vpids, gmap_lens, gmap_step_ids, gmap_pos_fts,
             gmap_pair_dists, gmap_vpids, bev_fts, bev_pos_fts, bev_masks, bev_nav_masks)
+        impl = Bk.MLMLossImpl(self.rt, self.mlm_head.eps, compute_loss)
+        pre = getattr(gmap_vpids, "host_mlm", None)      # ops.prepare_batch(): masked rows listed at collate time
+        if pre is not None and pre[0] == tuple(txt_labels.shape):
+            dev = txt_embeds.device
+            idx, labels = pre[1].to(dev, non_blocking=True), pre[2].to(dev, non_blocking=True)
+            masked_output = Bk.run_block(Bk.GatherRowsImpl(), [txt_embeds.reshape(-1, txt_embeds.shape[-1]), idx], [])
+            return Bk.run_block(impl, [masked_output, labels], self.mlm_head.params())
         sel = txt_labels != -1
         masked_output = self._masked_rows(txt_embeds, sel)
-        impl = Bk.MLMLossImpl(self.rt, self.mlm_head.eps, compute_loss)
         return Bk.run_block(impl, [masked_output, txt_labels[sel]], self.mlm_head.params())
 
     def forward_mrc(self, txt_ids, txt_lens, traj_view_img_fts, traj_obj_img_fts, traj_loc_fts, traj_nav_types,

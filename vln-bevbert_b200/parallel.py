@@ -44,3 +44,12 @@ def broadcast_parameters(model, src=0):
         return
     for t in list(model.parameters()) + list(model.buffers()):
         dist.broadcast(t.data, src)
+
+
+def direct_param_grads(enable=True):
+    """Let every encoder block write `p.grad` of its parameters itself at the end of its backward instead of returning
+    the gradients to autograd (one AccumulateGrad node per parameter, ~430 per step).  Same values in `p.grad`
+    (shared parameters are accumulated); tensor hooks on parameters -- and therefore torch DDP's bucket hooks -- do
+    not fire in this mode, so use it with FlatGradAllReduce or on a single GPU."""
+    from . import blocks
+    blocks.DIRECT_PARAM_GRADS = bool(enable)
