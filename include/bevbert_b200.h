@@ -88,6 +88,9 @@ int bb_bev_lift_index(const float* depths, const float* T_c2w, const float* S_w2
  * (bev_utils.py:412). counts int32 (B, D*D). Any of bev_f32 / bev_bf16 / ob_mask / counts may be NULL. */
 int bb_bev_scatter_mean_f32(const float* feats, const int32_t* cell_idx, int B, int P, int C, int ncell,
                             float* bev_f32, void* bev_bf16, uint8_t* ob_mask, int32_t* counts, void* stream);
+/* Same with bf16 point features (16-bit wire format of the grid features; sums and the mean stay fp32). */
+int bb_bev_scatter_mean_bf16(const void* feats_bf16, const int32_t* cell_idx, int B, int P, int C, int ncell,
+                             float* bev_f32, void* bev_bf16, uint8_t* ob_mask, int32_t* counts, void* stream);
 /* Same for the float64 semantic one-hots (bev_utils.py:417-423): mean, then sem>0 -> 1,
  * sem_mask u8 (B, D*D) = (sum over classes > 0). */
 int bb_bev_scatter_sem_f64(const double* sems, const int32_t* cell_idx, int B, int P, int S, int ncell,

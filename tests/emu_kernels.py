@@ -158,6 +158,7 @@ def bev_lift_index(depths, T_c2w, S_w2c, T_w2c, map_dim, map_res, depth_scale=10
 
 def bev_scatter_mean(feats, cell_idx, ncell, want_f32=True, want_bf16=True):
     from oracle import bevbert_ref as R
+    feats = feats.float()                      # bf16 wire features pool in fp32, like the kernel
     out = torch.stack([R.scatter_mean(feats[i], cell_idx[i].long(), ncell) for i in range(feats.shape[0])], 0)
     ob = ~((out.max(-1)[0] == 0) & (out.min(-1)[0] == 0))
     cnt = torch.stack([torch.bincount(cell_idx[i][cell_idx[i] >= 0].long(), minlength=ncell) for i in range(feats.shape[0])], 0)

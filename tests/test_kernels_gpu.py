@@ -94,6 +94,10 @@ def test_scatter_mean_deterministic_and_exact(K):
     assert not ob.cpu()[1].any() and float(o32[1].abs().max()) == 0.0
     o32b, _, _, _ = K.bev_scatter_mean(dev(feats), dev(idx), ncell)
     assert torch.equal(o32, o32b), "run-to-run deterministic"
+    # 16-bit wire format: bf16 point features pool exactly like their fp32 images (same fp32 sums, same order)
+    w32, w16, wob, wcnt = K.bev_scatter_mean(dev(feats.to(BF)), dev(idx), ncell)
+    x32, _, xob, _ = E.bev_scatter_mean(feats.to(BF).float(), idx, ncell)
+    assert torch.equal(w32.cpu(), x32) and torch.equal(wob.cpu(), xob) and torch.equal(wcnt.cpu(), rcnt)
     sems = torch.nn.functional.one_hot(torch.randint(0, 40, (B, P), generator=g), 40).double()
     s, sm = K.bev_scatter_sem(dev(sems), dev(idx), ncell)
     rs, rsm = E.bev_scatter_sem(sems, idx, ncell)

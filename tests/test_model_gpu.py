@@ -122,3 +122,26 @@ def test_dropout_training_step_runs_and_is_reproducible():
         rel_l2(model.bert.lang_encoder.layer[0].attention.self.query.weight.grad, g1) < 1e-3   # split-K atomics
     l3 = model(b, "sap").mean()
     assert float(l3) != float(l1)
+
+
+@pytest.mark.gpu
+def test_bf16_wire_format_matches_fp32_inputs():
+    """prepare_batch(wire_dtype=bf16): the large feature tensors travel as bf16; loss and gradients stay within the
+    bf16 activation noise of the fp32-input run (same weights, dropout off)."""
+    from bevbert_b200.model.ops import prepare_batch
+    cfg, scfg = small_config(), small_synth()
+    model = synth.det_init_(GlocalTextPathCMTPreTraining(cfg), seed=3).to(DEV).train()
+    for task in ("sap", "mlm"):
+        host = synth.make_batch(scfg, seed=21, task=task)
+        outs = []
+        for wire in (None, torch.bfloat16):
+            model.zero_grad(set_to_none=True)
+            b = synth.batch_to(prepare_batch(synth.clone_batch(host), wire_dtype=wire), DEV)
+            if wire is not None:
+                assert b["rgbs"].dtype == torch.bfloat16 and b["traj_view_img_fts"].dtype == torch.bfloat16
+            loss = model(b, task).mean()
+            loss.backward()
+            g = torch.cat([p.grad.reshape(-1) for p in model.parameters() if p.grad is not None])
+            outs.append((float(loss), g.clone()))
+        assert abs(outs[0][0] - outs[1][0]) <= 1e-2 * abs(outs[0][0])
+        assert rel_l2(outs[1][1], outs[0][1]) < 5e-2

@@ -677,7 +677,12 @@ class LinearLNImpl:
             xa[:, :Kd] = x2
             w = self.wc.get(p[0], pad_k=Kp)
         else:
-            xa = K.cast_to_act(x2, self.rt.ds.make(self.p_in)) if x2.dtype == torch.float32 else x2.contiguous()
+            if x2.dtype == torch.float32:
+                xa = K.cast_to_act(x2, self.rt.ds.make(self.p_in))
+            elif self.p_in > 0.0 and self.rt.ds.training and not x.requires_grad:
+                xa = K.dropout_act(x2.contiguous(), self.rt.ds.make(self.p_in))   # 16-bit wire features: dropout only
+            else:
+                xa = x2.contiguous()
             w = self.wc.get(p[0])
         y, _ = lin_fwd(xa, w, p[1].detach())
         o, _, mean, rstd = K.layernorm_fwd(y, None, p[2].detach(), p[3].detach(), self.eps)

@@ -88,8 +88,19 @@ __global__ void lift_index_kernel(const float* __restrict__ depths, const float*
 constexpr int SC_WARPS = 8;
 constexpr int SC_MAXV = 6;  // float4 per lane per pass -> 768 columns per pass
 
+// 4 consecutive features of a point row: fp32 (the reference's collate dtype) or bf16 (16-bit wire format: the grid
+// features are stored as 16-bit floats on disk and used as bf16 GEMM operands right after the pooling anyway)
+__device__ __forceinline__ float4 load_feat4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float4 load_feat4(const __nv_bfloat16* p) {
+  const uint2 raw = __ldg(reinterpret_cast<const uint2*>(p));
+  const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
+  const float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
+  return make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+
+template <typename FT>
 __global__ void __launch_bounds__(SC_WARPS * 32)
-scatter_mean_f32_kernel(const float* __restrict__ feats, const int32_t* __restrict__ cell_idx, int P, int C, int ncell,
+scatter_mean_f32_kernel(const FT* __restrict__ feats, const int32_t* __restrict__ cell_idx, int P, int C, int ncell,
                         float* __restrict__ bev_f32, __nv_bfloat16* __restrict__ bev_bf16,
                         uint8_t* __restrict__ ob_mask, int32_t* __restrict__ counts) {
   bb::pdl_wait();
@@ -102,7 +113,7 @@ scatter_mean_f32_kernel(const float* __restrict__ feats, const int32_t* __restri
   __syncthreads();
   const int cell = blockIdx.x * SC_WARPS + warp;
   if (cell >= ncell) return;
-  const float* fb = feats + (long long)b * P * C;
+  const FT* fb = feats + (long long)b * P * C;
   const long long orow = ((long long)b * ncell + cell) * C;
 
   float vmax = -INFINITY, vmin = INFINITY;
@@ -118,12 +129,12 @@ scatter_mean_f32_kernel(const float* __restrict__ feats, const int32_t* __restri
       while (m) {
         const int j = __ffs(m) - 1;
         m &= m - 1;
-        const float* rowp = fb + (long long)(base + j) * C + c0;
+        const FT* rowp = fb + (long long)(base + j) * C + c0;
         float4 t[SC_MAXV];
 #pragma unroll
         for (int i = 0; i < SC_MAXV; ++i) {
           const int col = i * 128 + lane * 4;
-          t[i] = (c0 + col < C) ? __ldg(reinterpret_cast<const float4*>(rowp + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          t[i] = (c0 + col < C) ? load_feat4(rowp + col) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
 #pragma unroll
         for (int i = 0; i < SC_MAXV; ++i) {
@@ -229,25 +240,36 @@ extern "C" int bb_bev_lift_index(const float* depths, const float* T_c2w, const 
   return check_launch("lift_index_kernel");
 }
 
-extern "C" int bb_bev_scatter_mean_f32(const float* feats, const int32_t* cell_idx, int B, int P, int C, int ncell,
-                                       float* bev_f32, void* bev_bf16, uint8_t* ob_mask, int32_t* counts,
-                                       void* stream) {
+template <typename FT>
+static int scatter_mean_launch(const FT* feats, const int32_t* cell_idx, int B, int P, int C, int ncell, float* bev_f32,
+                               void* bev_bf16, uint8_t* ob_mask, int32_t* counts, void* stream) {
   using namespace bb;
-  if (!feats || !cell_idx) return set_error("bb_bev_scatter_mean_f32: null argument");
-  if (C % 4 != 0) return set_error("bb_bev_scatter_mean_f32: C must be a multiple of 4");
-  if ((size_t)P * 4 > 200 * 1024) return set_error("bb_bev_scatter_mean_f32: too many points per sample for smem");
+  if (!feats || !cell_idx) return set_error("bb_bev_scatter_mean: null argument");
+  if (C % 4 != 0) return set_error("bb_bev_scatter_mean: C must be a multiple of 4");
+  if ((size_t)P * 4 > 200 * 1024) return set_error("bb_bev_scatter_mean: too many points per sample for smem");
   if (B <= 0) return 0;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(scatter_mean_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(scatter_sem_f64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(scatter_mean_f32_kernel<FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr_set = true;
   }
   dim3 grid((ncell + SC_WARPS - 1) / SC_WARPS, B);
-  bb::launch_pdl(scatter_mean_f32_kernel, grid, SC_WARPS * 32, (size_t)P * 4, (cudaStream_t)stream, 
+  bb::launch_pdl(scatter_mean_f32_kernel<FT>, grid, SC_WARPS * 32, (size_t)P * 4, (cudaStream_t)stream,
       feats, cell_idx, P, C, ncell, bev_f32, reinterpret_cast<__nv_bfloat16*>(bev_bf16), ob_mask, counts);
   count_launch();
   return check_launch("scatter_mean_f32_kernel");
+}
+
+extern "C" int bb_bev_scatter_mean_f32(const float* feats, const int32_t* cell_idx, int B, int P, int C, int ncell,
+                                       float* bev_f32, void* bev_bf16, uint8_t* ob_mask, int32_t* counts,
+                                       void* stream) {
+  return scatter_mean_launch(feats, cell_idx, B, P, C, ncell, bev_f32, bev_bf16, ob_mask, counts, stream);
+}
+extern "C" int bb_bev_scatter_mean_bf16(const void* feats, const int32_t* cell_idx, int B, int P, int C, int ncell,
+                                        float* bev_f32, void* bev_bf16, uint8_t* ob_mask, int32_t* counts,
+                                        void* stream) {
+  return scatter_mean_launch(reinterpret_cast<const __nv_bfloat16*>(feats), cell_idx, B, P, C, ncell, bev_f32, bev_bf16,
+                             ob_mask, counts, stream);
 }
 
 extern "C" int bb_bev_scatter_sem_f64(const double* sems, const int32_t* cell_idx, int B, int P, int S, int ncell,

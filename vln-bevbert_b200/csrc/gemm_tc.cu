@@ -266,16 +266,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + acc * 256;
-      // One 16-column chunk: r holds its accumulators (already waited for).  The TMEM load of the NEXT chunk is issued
-      // before this runs, so the tcgen05.ld round trip overlaps the arithmetic and stores of the current chunk.
-      auto process = [&](const int c, uint32_t (&r)[16], const uint4 (&qa)[2], const uint4 (&qd)[2]) {
+      for (int c = half * 16; c < p.block_n; c += 32) {
         const int col0 = n0 + c;
+        if (col0 >= p.N) break;  // warp-uniform
+        uint32_t r[16];
+        tmem_ld16(taddr + c, r);
+        // operands of this chunk (prefetched) -> locals, then start fetching the next chunk's
         __align__(16) __nv_bfloat16 ha[16], hd[16];
-        reinterpret_cast<uint4*>(ha)[0] = qa[0];
-        reinterpret_cast<uint4*>(ha)[1] = qa[1];
-        reinterpret_cast<uint4*>(hd)[0] = qd[0];
-        reinterpret_cast<uint4*>(hd)[1] = qd[1];
-        if (!row_ok) return;
+        reinterpret_cast<uint4*>(ha)[0] = pa[0];
+        reinterpret_cast<uint4*>(ha)[1] = pa[1];
+        reinterpret_cast<uint4*>(hd)[0] = pd[0];
+        reinterpret_cast<uint4*>(hd)[1] = pd[1];
+        prefetch(c + 32);
+        tmem_ld_wait();
+        if (!row_ok) continue;
         float v[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) * p.alpha;
@@ -377,26 +381,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               if (col0 + i < p.N) D[i] = __float2bfloat16(v[i]);
           }
         }
-            };
-      auto valid = [&](int c) { return c < p.block_n && n0 + c < p.N; };   // warp-uniform
-      uint32_t ra[16], rb[16];
-      int c = half * 16;
-      if (valid(c)) tmem_ld16(taddr + c, ra);
-      while (valid(c)) {
-        uint4 qa[2] = {pa[0], pa[1]}, qd[2] = {pd[0], pd[1]};
-        prefetch(c + 32);
-        tmem_ld_wait_regs(ra);
-        const bool nb = valid(c + 32);
-        if (nb) tmem_ld16(taddr + c + 32, rb);
-        process(c, ra, qa, qd);
-        if (!nb) break;
-        c += 32;
-        uint4 qa2[2] = {pa[0], pa[1]}, qd2[2] = {pd[0], pd[1]};
-        prefetch(c + 32);
-        tmem_ld_wait_regs(rb);
-        if (valid(c + 32)) tmem_ld16(taddr + c + 32, ra);
-        process(c, rb, qa2, qd2);
-        c += 32;
       }
       tc_fence_before();
       __syncwarp();

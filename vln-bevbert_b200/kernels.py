@@ -251,18 +251,21 @@ def bev_lift_index(depths, T_c2w, S_w2c, T_w2c, map_dim, map_res, depth_scale=10
 
 
 def bev_scatter_mean(feats, cell_idx, ncell, want_f32=True, want_bf16=True):
-    """feats f32 (B,P,C) -> (bev_f32 | None, bev_bf16 | None, ob_mask bool (B,ncell), counts int32)."""
+    """feats f32 or bf16 (B,P,C) -> (bev_f32 | None, bev_bf16 | None, ob_mask bool (B,ncell), counts int32)."""
     lib = _lib.load()
-    _req(feats, torch.float32, "feats")
+    if feats.dtype != BF16:
+        _req(feats, torch.float32, "feats")
+    elif not feats.is_cuda:
+        raise RuntimeError("feats must be a CUDA tensor (the hot path has no CPU implementation)")
+    fn = lib.bb_bev_scatter_mean_bf16 if feats.dtype == BF16 else lib.bb_bev_scatter_mean_f32
     B, P, Cc = feats.shape
     dev = feats.device
     o32 = torch.empty(B, ncell, Cc, dtype=torch.float32, device=dev) if want_f32 else None
     o16 = torch.empty(B, ncell, Cc, dtype=BF16, device=dev) if want_bf16 else None
     ob = torch.empty(B, ncell, dtype=torch.uint8, device=dev)
     cnt = torch.empty(B, ncell, dtype=torch.int32, device=dev)
-    _lib.check(lib.bb_bev_scatter_mean_f32(feats.contiguous().data_ptr(), cell_idx.data_ptr(), B, P, Cc, ncell,
-                                           _p(o32), _p(o16), ob.data_ptr(), cnt.data_ptr(), _stream()),
-               "bb_bev_scatter_mean_f32")
+    _lib.check(fn(feats.contiguous().data_ptr(), cell_idx.data_ptr(), B, P, Cc, ncell,
+                  _p(o32), _p(o16), ob.data_ptr(), cnt.data_ptr(), _stream()), "bb_bev_scatter_mean")
     return o32, o16, ob.bool(), cnt
 
 

@@ -98,12 +98,16 @@ class PreparedList(list):
     host_mlm = None
 
 
-def prepare_batch(batch):
+WIRE_KEYS = ("rgbs", "traj_view_img_fts", "traj_obj_img_fts")
+
+
+def prepare_batch(batch, wire_dtype=None):
     """Optional collate-time step (the reference's `sap_collate` / `mlm_collate` run in DataLoader workers,
     pretrain_src/data/tasks.py:118-160): does the string matching behind the topological-map aggregation and the
     SAP logit fusion once, on the host, into pinned index tensors attached to `batch['gmap_vpids']`.  forward()
     finds and uses them; without this call it builds the same tensors itself (same results, more host time
-    inside the step)."""
+    inside the step).  `wire_dtype=torch.bfloat16` additionally converts the large fp32 feature tensors (WIRE_KEYS)
+    to bf16 on the host; the model accepts either dtype."""
     gv = PreparedList(batch["gmap_vpids"])
     G = batch["gmap_step_ids"].shape[1]
     Vtot = batch["traj_loc_fts"].shape[1]
@@ -124,6 +128,14 @@ def prepare_batch(batch):
         gv.host_mlm = (tuple(lab.shape), idx.pin_memory() if pin else idx, sel.pin_memory() if pin else sel)
     out = dict(batch)
     out["gmap_vpids"] = gv
+    if wire_dtype is not None:
+        # 16-bit wire format for the large feature tensors (the grid / view features are stored as 16-bit floats in the
+        # reference's HDF5 files and are bf16 GEMM operands on the device): halves the host->device bytes per step
+        for k in WIRE_KEYS:
+            v = out.get(k)
+            if torch.is_tensor(v) and v.dtype == torch.float32:
+                v = v.to(wire_dtype)
+                out[k] = v.pin_memory() if pin else v
     return out
 
 
