@@ -34,8 +34,13 @@ def _worker(rank, world, port, task, ret, mode="ddp"):
     else:       # bevbert_b200.parallel: one flat all-reduce after backward (what bench.py runs at N > 1)
         from bevbert_b200.parallel import FlatGradAllReduce, broadcast_parameters
         broadcast_parameters(model)
-        model(shard, task).mean().backward()
-        FlatGradAllReduce(model.parameters(), world)()
+        reducer = FlatGradAllReduce(model.parameters(), world)
+        for _ in range(2):      # the second step runs on the step arena (reduced in place), the first on the fallback
+            model.zero_grad(set_to_none=True)
+            model(synth.clone_batch(shard), task).mean().backward()
+            reducer()
+        from bevbert_b200 import blocks
+        assert blocks.ARENA.buf is not None and blocks.ARENA.off > 0
     grads = {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None}
     if rank == 0:
         single = synth.det_init_(GlocalTextPathCMTPreTraining(cfg), seed=3).train()

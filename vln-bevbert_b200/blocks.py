@@ -50,6 +50,7 @@ class Runtime:
         self.ds = DropState(training, self.calls * 7919 + 17 if seed is None else seed)
         if training:
             ARENA.new_step(tag)
+            SCRATCH.new_step(tag)
         return self.ds
 
 
@@ -135,15 +136,17 @@ class _ZeroArena:
         return torch.zeros(n4, dtype=torch.float32, device=device)
 
 
-ARENA = _ZeroArena()
+ARENA = _ZeroArena()      # parameter gradients only: same carve order and sizes on every data-parallel rank
+SCRATCH = _ZeroArena()    # everything else that must start at zero (activation gradients, graph-bias gradient)
 
 
-def zeros_f32(device, *shape):
-    """zero-filled fp32 tensor of `shape` from the step arena (for accumulate-into gradient buffers)."""
+def zeros_f32(device, *shape, scratch=False):
+    """zero-filled fp32 tensor of `shape` from the step arena: ARENA for accumulate-into PARAMETER gradients (so that
+    parallel.FlatGradAllReduce can reduce the arena in place), SCRATCH for data-dependent-size buffers."""
     n = 1
     for d in shape:
         n *= d
-    return ARENA.take(device, n)[:n].view(shape)
+    return (SCRATCH if scratch else ARENA).take(device, n)[:n].view(shape)
 
 
 class ZeroPool:
@@ -310,9 +313,9 @@ def attn_sublayer_bwd(st, wc, dy, p, H, want_dbias=False):
     cross = st["cross"]
     shapes = [(Hd,), (Hd,), (Hd, Hd), (Hd,)]                       # dgamma, dbeta, dWo, dbo
     shapes += [(Hd, Hd), (Hd,), (2 * Hd, Hd), (2 * Hd,)] if cross else [(3 * Hd, Hd), (3 * Hd,)]
-    if want_dbias:
-        shapes.append((B, nq, nk))
     z = ZeroPool(dev, *shapes).out
+    if want_dbias:
+        z = z + [zeros_f32(dev, B, nq, nk, scratch=True)]      # activation gradient: its size depends on the batch
     dg, db, dWo, dbo = z[0], z[1], z[2], z[3]
     dbias = z[-1] if want_dbias else None
     dao, dres = K.layernorm_bwd(dy.reshape(-1, Hd), ao, x2, p[8].detach(), st["mean"], st["rstd"], drop_in=st["hdrop"],
@@ -428,9 +431,9 @@ def attn_native_bwd(st, dy, want_dbias=False):
         dy = dy.contiguous()
     shapes = [(Hd,), (Hd,), (Hd, Hd), (Hd,)]
     shapes += [(Hd, Hd), (Hd,), (2 * Hd, Hd), (2 * Hd,)] if cross else [(3 * Hd, Hd), (3 * Hd,)]
-    if want_dbias:
-        shapes.append((B, nq, nk))
     z = ZeroPool(dev, *shapes).out
+    if want_dbias:
+        z = z + [zeros_f32(dev, B, nq, nk, scratch=True)]      # activation gradient: its size depends on the batch
     gws = _ws(st["a_bwd"], dev)
     dx = torch.empty(B * nq, Hd, dtype=K.act_dtype(), device=dev)
     dc = torch.empty(B * nk, Hd, dtype=K.act_dtype(), device=dev) if cross else None
@@ -810,7 +813,7 @@ class SegmentSumImpl:
     def bwd(self, st, gouts, p):
         seg_off, idx, w, nseg = st["seg"]
         Hd = st["sshape"][-1]
-        d32 = zeros_f32(gouts[0].device, *st["sshape"])
+        d32 = zeros_f32(gouts[0].device, *st["sshape"], scratch=True)
         K.segment_wsum_bwd(gouts[0].contiguous(), seg_off, idx, w, nseg, Hd, d32)
         return [K.cast_to_act(d32), None, None, None], []
 
@@ -826,7 +829,7 @@ class GatherRowsImpl:
 
     def bwd(self, st, gouts, p):
         Hd = st["sshape"][-1]
-        d32 = zeros_f32(gouts[0].device, *st["sshape"])
+        d32 = zeros_f32(gouts[0].device, *st["sshape"], scratch=True)
         K.scatter_add_rows(gouts[0].contiguous(), st["idx"], Hd, d32.view(-1, Hd))
         return [K.cast_to_act(d32), None], []
 

@@ -13,7 +13,12 @@ import torch.distributed as dist
 
 
 class FlatGradAllReduce:
-    """all-reduce (average) the gradients of `params` through one flat buffer per step."""
+    """all-reduce (average) the gradients of `params` with one NCCL call per step.
+
+    From the second step of a task on, the blocks carve every gradient buffer from one zero-filled fp32 arena per step
+    (blocks._ZeroArena), in the same order on every rank, so the arena itself is the flat bucket and is reduced in
+    place.  Gradients that live elsewhere (the first step of a task, the few small heads that run on torch autograd)
+    go through a second, small flat buffer."""
 
     def __init__(self, params, world_size=None):
         self.params = [p for p in params if p.requires_grad]
@@ -24,18 +29,31 @@ class FlatGradAllReduce:
     def __call__(self):
         if self.world == 1:
             return
+        from . import blocks
+        arena = blocks.ARENA.buf
         grads = [p.grad for p in self.params if p.grad is not None]
         if not grads:
             return
-        n = sum(g.numel() for g in grads)
+        inv = 1.0 / self.world
+        if arena is not None and blocks.ARENA.off > 0:
+            base = arena.untyped_storage().data_ptr()
+            rest = [g for g in grads if g.untyped_storage().data_ptr() != base]
+            used = arena[:blocks.ARENA.off]
+            used.mul_(inv)
+            dist.all_reduce(used)
+        else:
+            rest = grads
+        if not rest:
+            return
+        n = sum(g.numel() for g in rest)
         if self.buf is None or self.buf.numel() < n:
-            self.buf = torch.empty(n, dtype=torch.float32, device=grads[0].device)
+            self.buf = torch.empty(n, dtype=torch.float32, device=rest[0].device)
         flat = self.buf[:n]
-        views = list(torch.split(flat, [g.numel() for g in grads]))
-        torch._foreach_copy_(views, [g.reshape(-1) for g in grads])
-        flat.mul_(1.0 / self.world)
+        views = list(torch.split(flat, [g.numel() for g in rest]))
+        torch._foreach_copy_(views, [g.reshape(-1) for g in rest])
+        flat.mul_(inv)
         dist.all_reduce(flat)
-        torch._foreach_copy_([g.view(-1) if g.is_contiguous() else g.reshape(-1) for g in grads], views)
+        torch._foreach_copy_([g.view(-1) if g.is_contiguous() else g.reshape(-1) for g in rest], views)
 
 
 def broadcast_parameters(model, src=0):
