@@ -66,6 +66,9 @@ int bb_gemm_bf16(const bb_gemm_args* args, void* stream);
 /* Optional measurement hook (bench.py roofline): while enabled, every bb_gemm_bf16 launch is bracketed by a pair
  * of CUDA events on its stream.  bb_gemm_profile(1) resets and starts, (0) stops; _count() = launches recorded;
  * _read(i, &ms, dims) synchronises on launch i and returns its duration and (M, N, K, batches, a_mn, b_mn). */
+/* Debug: when device_buf is not NULL every bb_gemm_bf16 launch writes, per CTA c and local tile i < 16, four
+ * %globaltimer stamps at device_buf[(c*16+i)*4 + {0: MMA issue start, 1: MMA issue end, 2: epilogue start, 3: end}]. */
+int bb_gemm_trace(long long* device_buf);
 int bb_gemm_profile(int enable);
 int64_t bb_gemm_profile_count(void);
 int bb_gemm_profile_read(int64_t idx, float* ms, int64_t* dims6);

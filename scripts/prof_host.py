@@ -14,7 +14,12 @@ from bevbert_b200.model.pretrain_cmt import GlocalTextPathCMTPreTraining  # noqa
 
 dev = torch.device("cuda", 0)
 model = synth.det_init_(GlocalTextPathCMTPreTraining(full_config()), seed=3).to(dev).train()
-opt = torch.optim.AdamW(model.parameters(), lr=5e-5, fused=True)
+from bevbert_b200.optim import FusedAdamW  # noqa: E402
+from bevbert_b200.parallel import direct_param_grads  # noqa: E402
+direct_param_grads(True)
+opt = FusedAdamW(model.parameters(), lr=5e-5)
+import gc  # noqa: E402
+gc.collect(); gc.freeze(); gc.disable()
 from bevbert_b200.model.ops import prepare_batch  # noqa: E402
 batches = {t: synth.batch_to(prepare_batch(synth.make_batch(synth.SynthConfig(batch_size=32), seed=1, task=t)), dev) for t in set(MIX)}
 
@@ -22,7 +27,6 @@ batches = {t: synth.batch_to(prepare_batch(synth.make_batch(synth.SynthConfig(ba
 def step(t):
     model(batches[t], t).mean().backward()
     opt.step()
-    opt.zero_grad(set_to_none=True)
 
 
 for i in range(6):
@@ -45,4 +49,5 @@ for i in range(11):
 torch.cuda.synchronize()
 pr.disable()
 ps = pstats.Stats(pr)
-ps.sort_stats("tottime").print_stats(35)
+ps.sort_stats("tottime").print_stats(30)
+ps.sort_stats("cumtime").print_stats(40)

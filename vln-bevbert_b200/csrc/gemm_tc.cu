@@ -52,7 +52,15 @@ struct GemmKParams {
   unsigned long long drop_seed;
   unsigned int drop_thresh;
   float drop_scale;
+  int fast_gelu;      // experiment: Abramowitz-Stegun erf on approximate MUFU ops instead of erff()
+  long long* trace;   // debug: per CTA and local tile 4 globaltimer stamps (mma start/end, epilogue start/end) or null
 };
+
+__device__ __forceinline__ long long gtimer() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 
 struct TileCoord {
   int split, b1, b2, m_tile, n_tile;
@@ -187,6 +195,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
+        const int lt = (tile - tile0) / tile_step;
+        if (p.trace && lt < 16) p.trace[((long long)blockIdx.x * 16 + lt) * 4 + 0] = gtimer();
         const uint32_t d_tmem = tmem_base + acc * 256;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
@@ -213,6 +223,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         // accumulator complete -> epilogue (of both CTAs)
         if (CTAS == 2) umma_commit_2sm(&tmem_full[acc]);
         else umma_commit(&tmem_full[acc]);
+        if (p.trace && lt < 16) p.trace[((long long)blockIdx.x * 16 + lt) * 4 + 1] = gtimer();   // issue done (not retired)
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
@@ -265,6 +276,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
+      const int lt = (tile - tile0) / tile_step;
+      if (p.trace && lt < 16 && warp == 2 && lane == 0) p.trace[((long long)blockIdx.x * 16 + lt) * 4 + 2] = gtimer();
       const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + acc * 256;
       for (int c = half * 16; c < p.block_n; c += 32) {
         const int col0 = n0 + c;
@@ -310,8 +323,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           }
         }
         if (p.act == 1) {
+          if (p.fast_gelu) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = gelu_erf(v[i]);
+            for (int i = 0; i < 16; ++i) v[i] = gelu_fast(v[i]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = gelu_erf(v[i]);
+          }
         } else if (p.act == 2) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.0f);
@@ -325,8 +343,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             for (int i = 0; i < 16; ++i) a[i] = (col0 + i < p.N) ? bf2f(p.aux_in[off + i]) : 0.0f;
           }
           if (p.epi_mul == 1) {
+            if (p.fast_gelu) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] *= dgelu_erf(a[i]);
+              for (int i = 0; i < 16; ++i) v[i] *= dgelu_fast(a[i]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] *= dgelu_erf(a[i]);
+            }
           } else {
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] = a[i] > 0.0f ? v[i] : 0.0f;
@@ -384,6 +407,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       }
       tc_fence_before();
       __syncwarp();
+      if (p.trace && lt < 16 && warp == 2 && lane == 0) p.trace[((long long)blockIdx.x * 16 + lt) * 4 + 3] = gtimer();
       if (lane == 0) {
         if (CTAS == 2) mbar_arrive_leader(&tmem_empty[acc]);
         else mbar_arrive(&tmem_empty[acc]);
@@ -461,6 +485,7 @@ static bool g_prof_on = false;
 static std::vector<ProfRec> g_prof;
 static size_t g_prof_used = 0;
 
+static long long* g_trace = nullptr;   // bb_gemm_trace(): device buffer of (grid x 16 x 4) timestamps, debug only
 static int g_num_sms = 0;
 static int g_smem_optin = 0;
 
@@ -590,6 +615,15 @@ extern "C" int bb_gemm_bf16(const bb_gemm_args* a, void* stream_) {
   p.drop_seed = a->drop_seed;
   p.drop_thresh = a->drop_thresh;
   p.drop_scale = a->drop_scale;
+  p.trace = g_trace;
+  {
+    static int fg = -1;
+    if (fg < 0) {
+      const char* e_ = getenv("BB_FAST_GELU");
+      fg = (e_ && e_[0] == '1') ? 1 : 0;
+    }
+    p.fast_gelu = fg;
+  }
   if (p.epi_mul && !p.aux_in) return set_error("bb_gemm_bf16: epi_mul needs aux_in");
   // vector epilogue only when every row segment of 16 outputs is 16-byte aligned (for bf16: 8 elements)
   {
@@ -648,6 +682,11 @@ extern "C" int bb_gemm_bf16(const bb_gemm_args* a, void* stream_) {
   if (rec) cudaEventRecord(rec->e1, stream);
   count_launch();
   return check_launch("gemm_tc_kernel");
+}
+
+extern "C" int bb_gemm_trace(long long* device_buf) {
+  bb::g_trace = device_buf;
+  return 0;
 }
 
 extern "C" int bb_gemm_profile(int enable) {

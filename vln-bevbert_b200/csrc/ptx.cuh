@@ -234,8 +234,39 @@ __device__ __forceinline__ float dgelu_erf(float x) {
   const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
   return cdf + x * pdf;
 }
-// (a branch-free Abramowitz-Stegun erf with rcp + ex2 was tried in the GEMM epilogue and measured 25-45 % SLOWER than
-//  erff() on the FFN1 / gelu' products: erff's small-argument branch is a short polynomial with no special function.)
+// Experiment (BB_FAST_GELU=1): Abramowitz-Stegun 7.1.26 erf (|err| < 1.5e-7) on the approximate MUFU ops -- 14
+// instructions, branch-free.  (The same formula on __frcp_rn / exp2f measured 25-45 % SLOWER than erff().)
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float erf_as(float x, float& e_out) {
+  const float ax = fabsf(x);
+  const float t = rcp_approx(fmaf(0.3275911f, ax, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  poly *= t;
+  const float e = ex2_approx(-1.4426950408889634f * ax * ax);   // exp(-x^2)
+  e_out = e;
+  return copysignf(fmaf(-poly, e, 1.0f), x);
+}
+__device__ __forceinline__ float gelu_fast(float x) {
+  float e;
+  return x * 0.5f * (1.0f + erf_as(x * 0.70710678118654752440f, e));
+}
+__device__ __forceinline__ float dgelu_fast(float x) {
+  float e;   // exp(-x^2/2), shared by the pdf term
+  const float cdf = 0.5f * (1.0f + erf_as(x * 0.70710678118654752440f, e));
+  return fmaf(x * 0.39894228040143267794f, e, cdf);
+}
 
 // Counter-based RNG for dropout: 32 random bits from (seed, 64-bit element index) with a 32-bit avalanche hash
 // (two multiply-xorshift rounds); stateless, so backward regenerates the identical mask.  Kept cheap on purpose:

@@ -181,6 +181,31 @@ static int run_case(const Case& c) {
     cudaEventElapsedTime(&ms, e0, e1);
     ms /= c.timing_iters;
   }
+  if (getenv("BB_GEMM_TRACE") && c.timing_iters > 0 && ok) {
+    // per-tile timeline of one warm launch: MMA issue window and epilogue window of the first tiles of a few CTAs
+    const int ncta = 160;
+    long long* dT;
+    CK(cudaMalloc(&dT, (size_t)ncta * 16 * 4 * 8));
+    CK(cudaMemset(dT, 0, (size_t)ncta * 16 * 4 * 8));
+    bb_gemm_trace(dT);
+    bb_gemm_bf16(&g, nullptr);
+    CK(cudaDeviceSynchronize());
+    bb_gemm_trace(nullptr);
+    std::vector<long long> hT((size_t)ncta * 16 * 4);
+    CK(cudaMemcpy(hT.data(), dT, hT.size() * 8, cudaMemcpyDeviceToHost));
+    long long t0 = 0;
+    for (long long v : hT) if (v && (!t0 || v < t0)) t0 = v;
+    for (int cta : {0, 1, 2, 73, 147}) {
+      printf("   trace cta %3d:", cta);
+      for (int i = 0; i < 16; ++i) {
+        const long long* r = &hT[((size_t)cta * 16 + i) * 4];
+        if (!r[0] && !r[2]) break;
+        printf(" [mma %.2f-%.2f epi %.2f-%.2f]", (r[0] - t0) * 1e-3, (r[1] - t0) * 1e-3, (r[2] - t0) * 1e-3, (r[3] - t0) * 1e-3);
+      }
+      printf("\n");
+    }
+    cudaFree(dT);
+  }
   double tflops = ms > 0 ? 2.0 * c.M * c.N * c.K * nb / (ms * 1e-3) / 1e12 : 0;
   printf("CASE %-22s %s max_err=%.4g (at %lld) max_ref=%.4g aux_err=%.4g stray=%lld  %.3f ms %.1f TFLOP/s\n", c.name,
          ok ? "PASS" : "FAIL", max_err, bad_i, max_ref, max_aux_err, stray, ms, tflops);
