@@ -29,6 +29,9 @@ constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
 constexpr int NUM_THREADS = 320;  // 1 TMA warp + 1 MMA warp + 8 epilogue warps
 constexpr int MAX_STAGES = 8;
 constexpr int TMEM_COLS = 512;
+constexpr int STAGE_ROW_BYTES = 144;                     // 128 B of a row + 16 B pad (conflict-free 16-byte accesses)
+constexpr int STAGE_WARP_BYTES = 16 * STAGE_ROW_BYTES;   // 16 rows per pass
+constexpr int STAGE_BYTES = 8 * STAGE_WARP_BYTES;        // 18 KB for the 8 epilogue warps
 
 struct GemmKParams {
   int M, N, K;
@@ -52,6 +55,7 @@ struct GemmKParams {
   unsigned long long drop_seed;
   unsigned int drop_thresh;
   float drop_scale;
+  int staged;         // coalesced epilogue stores through the smem staging area (BB_GEMM_STAGED=0 turns it off)
   int fast_gelu;      // experiment: Abramowitz-Stegun erf on approximate MUFU ops instead of erff()
   long long* trace;   // debug: per CTA and local tile 4 globaltimer stamps (mma start/end, epilogue start/end) or null
 };
@@ -85,7 +89,12 @@ __device__ __forceinline__ float bf2f(__nv_bfloat16 v) { return __bfloat162float
 // CTAS = 1: one CTA per 128 x block_n tile.  CTAS = 2: a CTA pair (cluster of 2 on one TPC) per 256 x block_n tile with
 // tcgen05.mma.cta_group::2 -- each CTA stages its 128 rows of A and half of the B tile, the leader issues the MMAs,
 // every CTA runs the epilogue of its own 128 accumulator rows.
-template <int CTAS>
+// EPI selects the epilogue at compile time: 0 = every feature (activation, second output, gelu'/relu' multiply,
+// dropout, residual add, any store), 1 = plain (alpha, optional bias, bf16 or fp32 store), 2 = fp32 atomic accumulate
+// (split-K weight gradients).  The specialised variants drop the operand-prefetch registers and feature branches of
+// the generic path: a per-tile timestamp trace showed the generic epilogue at ~7 us per 128x256 tile against a 4.7 us
+// mainloop at K = 768, i.e. every K = 768 product was epilogue-bound.
+template <int CTAS, int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const GemmKParams p, int total_tiles) {
@@ -103,6 +112,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
   float* sbias = reinterpret_cast<float*>(smem + p.stages * stage_bytes + 512);  // [2][256], one per accumulator
+  uint8_t* sstage = smem + p.stages * stage_bytes + 512 + 2048;                   // epilogue store staging, 8 warps
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -237,8 +247,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int half = (warp - 2) >> 2;
     int acc = 0;
     uint32_t acc_phase = 0;
-    const bool need_aux = p.epi_mul != 0;
-    const bool need_add = p.add_in != nullptr;
+    const bool need_aux = EPI == 0 && p.epi_mul != 0;
+    const bool need_add = EPI == 0 && p.add_in != nullptr;
+    const bool has_aux_out = EPI == 0 && p.aux_out != nullptr;
+    const int act = EPI == 0 ? p.act : 0;
+    const unsigned int drop_thresh = EPI == 0 ? p.drop_thresh : 0u;
+    const bool out_f32 = EPI == 2 ? true : (p.out_f32 != 0);
+    const bool atomic = EPI == 2 ? true : (EPI == 1 ? false : p.atomic != 0);
     for (int tile = tile0; tile < total_tiles; tile += tile_step) {
       const TileCoord t = decode_tile(p, tile);
       const int row = (t.m_tile * CTAS + rank) * BLOCK_M + quarter * 32 + lane;
@@ -279,6 +294,151 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const int lt = (tile - tile0) / tile_step;
       if (p.trace && lt < 16 && warp == 2 && lane == 0) p.trace[((long long)blockIdx.x * 16 + lt) * 4 + 2] = gtimer();
       const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + acc * 256;
+      if constexpr (EPI != 0) {
+        // Specialised epilogues: 32-column TMEM loads, the next one in flight while the current 32 columns are
+        // scaled / biased / converted / stored.  Warp `half` takes every other 32-column chunk.
+        auto emit = [&](const uint32_t* r, const int c) {   // 16 columns starting at tile column c
+          const int col0 = n0 + c;
+          if (c >= p.block_n || col0 >= p.N || !row_ok) return;
+          float v[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) * p.alpha;
+          if (add_bias) {
+            const float4* sb4 = reinterpret_cast<const float4*>(sbias + acc * 256 + c);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float4 bv = sb4[i];
+              v[4 * i] += bv.x;
+              v[4 * i + 1] += bv.y;
+              v[4 * i + 2] += bv.z;
+              v[4 * i + 3] += bv.w;
+            }
+          }
+          const bool full = (col0 + 16 <= p.N) && p.vec_ok;
+          const long long off = row_off + col0;
+          if (out_f32) {
+            float* D = reinterpret_cast<float*>(p.D) + off;
+            if (atomic) {
+              if (full) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(D + 4 * i), "f"(v[4 * i]),
+                               "f"(v[4 * i + 1]), "f"(v[4 * i + 2]), "f"(v[4 * i + 3])
+                               : "memory");
+              } else {
+                for (int i = 0; i < 16; ++i)
+                  if (col0 + i < p.N) atomicAdd(D + i, v[i]);
+              }
+            } else if (full) {
+              float4* dst = reinterpret_cast<float4*>(D);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+            } else {
+              for (int i = 0; i < 16; ++i)
+                if (col0 + i < p.N) D[i] = v[i];
+            }
+          } else {
+            __nv_bfloat16* D = reinterpret_cast<__nv_bfloat16*>(p.D) + off;
+            if (full) {
+              __align__(16) __nv_bfloat162 h[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+              uint4* dst = reinterpret_cast<uint4*>(D);
+              dst[0] = reinterpret_cast<uint4*>(h)[0];
+              dst[1] = reinterpret_cast<uint4*>(h)[1];
+            } else {
+              for (int i = 0; i < 16; ++i)
+                if (col0 + i < p.N) D[i] = __float2bfloat16(v[i]);
+            }
+          }
+        };
+        // Slabs of 128 output bytes per row (64 bf16 or 32 fp32 columns); warp `half` takes every other slab.
+        // A lane owns one ROW of the accumulator, so storing straight from registers makes every store instruction
+        // touch 32 different 128-byte lines with 16 bytes each (the trace showed the epilogue bound by exactly that:
+        // ~6 us per 128x256 tile against a 4.7 us mainloop).  Each slab therefore goes through a per-warp shared
+        // memory staging area (16 rows x 144 B, two passes) and leaves as full 128-byte row segments: 4 lines per
+        // store instruction instead of 32.
+        const int W = out_f32 ? 32 : 64;
+        uint8_t* stg = sstage + (warp - 2) * STAGE_WARP_BYTES;
+        const int tile_row0 = (t.m_tile * CTAS + rank) * BLOCK_M + quarter * 32;
+        const long long batch_off = (long long)t.b1 * p.d_s1 + (long long)t.b2 * p.d_s2;
+        for (int c = half * W; c < p.block_n; c += 2 * W) {
+          const int col0 = n0 + c;
+          if (col0 >= p.N) break;   // warp-uniform
+          uint32_t r[64];
+          {
+            uint32_t(&r0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&r[0]);
+            uint32_t(&r1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&r[32]);
+            tmem_ld32(taddr + c, r0);
+            if (!out_f32) {
+              tmem_ld32(taddr + c + 32, r1);
+              tmem_ld_wait32(r1);
+            }
+            tmem_ld_wait32(r0);
+          }
+          if (!(p.staged && p.vec_ok && col0 + W <= p.N && c + W <= p.block_n)) {   // ragged slab: direct stores
+            for (int k = 0; k < W / 16; ++k) emit(r + 16 * k, c + 16 * k);
+            continue;
+          }
+          uint4 pk[8];
+          if (out_f32) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float4 v = make_float4(__uint_as_float(r[4 * j]) * p.alpha, __uint_as_float(r[4 * j + 1]) * p.alpha,
+                                     __uint_as_float(r[4 * j + 2]) * p.alpha, __uint_as_float(r[4 * j + 3]) * p.alpha);
+              if (add_bias) {
+                const float4 bv = *reinterpret_cast<const float4*>(sbias + acc * 256 + c + 4 * j);
+                v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+              }
+              pk[j] = *reinterpret_cast<uint4*>(&v);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float v[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[8 * j + i]) * p.alpha;
+              if (add_bias) {
+                const float4 b0 = *reinterpret_cast<const float4*>(sbias + acc * 256 + c + 8 * j);
+                const float4 b1 = *reinterpret_cast<const float4*>(sbias + acc * 256 + c + 8 * j + 4);
+                v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+                v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+              }
+              __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
+              __nv_bfloat162 h2 = __floats2bfloat162_rn(v[4], v[5]), h3 = __floats2bfloat162_rn(v[6], v[7]);
+              pk[j] = make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
+                                 *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
+            }
+          }
+          uint8_t* gbase = reinterpret_cast<uint8_t*>(p.D) + (batch_off + col0) * (out_f32 ? 4 : 2);
+          const long long row_bytes = p.ldd * (out_f32 ? 4 : 2);
+#pragma unroll
+          for (int pass = 0; pass < 2; ++pass) {
+            if ((lane >> 4) == pass) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) *reinterpret_cast<uint4*>(stg + (lane & 15) * STAGE_ROW_BYTES + j * 16) = pk[j];
+            }
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int rr = k * 4 + (lane >> 3), ch = lane & 7;
+              const uint4 val = *reinterpret_cast<const uint4*>(stg + rr * STAGE_ROW_BYTES + ch * 16);
+              const int grow = tile_row0 + pass * 16 + rr;
+              if (grow < p.M) {
+                uint8_t* dst = gbase + grow * row_bytes + ch * 16;
+                if (atomic) {
+                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(__uint_as_float(val.x)),
+                               "f"(__uint_as_float(val.y)), "f"(__uint_as_float(val.z)), "f"(__uint_as_float(val.w))
+                               : "memory");
+                } else {
+                  *reinterpret_cast<uint4*>(dst) = val;
+                }
+              }
+            }
+            __syncwarp();
+          }
+        }
+      } else
       for (int c = half * 16; c < p.block_n; c += 32) {
         const int col0 = n0 + c;
         if (col0 >= p.N) break;  // warp-uniform
@@ -309,7 +469,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           }
         }
         const long long off = row_off + col0;
-        if (p.aux_out != nullptr) {
+        if (has_aux_out) {
           if (full && p.vec_ok) {
             __align__(16) __nv_bfloat162 h[8];
 #pragma unroll
@@ -322,7 +482,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               if (col0 + i < p.N) p.aux_out[off + i] = __float2bfloat16(v[i]);
           }
         }
-        if (p.act == 1) {
+        if (act == 1) {
           if (p.fast_gelu) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] = gelu_fast(v[i]);
@@ -330,7 +490,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] = gelu_erf(v[i]);
           }
-        } else if (p.act == 2) {
+        } else if (act == 2) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.0f);
         }
@@ -355,10 +515,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             for (int i = 0; i < 16; ++i) v[i] = a[i] > 0.0f ? v[i] : 0.0f;
           }
         }
-        if (p.drop_thresh != 0) {
+        if (drop_thresh != 0) {
 #pragma unroll
           for (int i = 0; i < 16; ++i)
-            v[i] = drop_keep(p.drop_seed, (uint64_t)(off + i), p.drop_thresh) ? v[i] * p.drop_scale : 0.0f;
+            v[i] = drop_keep(p.drop_seed, (uint64_t)(off + i), drop_thresh) ? v[i] * p.drop_scale : 0.0f;
         }
         if (need_add) {
           if (full && p.vec_ok) {
@@ -369,9 +529,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               if (col0 + i < p.N) v[i] += bf2f(p.add_in[off + i]);
           }
         }
-        if (p.out_f32) {
+        if (out_f32) {
           float* D = reinterpret_cast<float*>(p.D) + off;
-          if (p.atomic) {
+          if (atomic) {
             if (full && p.vec_ok) {
 #pragma unroll
               for (int i = 0; i < 4; ++i)
@@ -495,9 +655,13 @@ static int init_device_info() {
   if (cudaGetDevice(&dev) != cudaSuccess) return set_error("cudaGetDevice failed");
   cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
   cudaDeviceGetAttribute(&g_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-  if (cudaFuncSetAttribute(gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin) != cudaSuccess ||
-      cudaFuncSetAttribute(gemm_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin) != cudaSuccess)
-    return set_error("cudaFuncSetAttribute(max dynamic smem) failed for gemm_tc_kernel");
+  bool ok = true;
+  auto set = [&](auto kernel) {
+    ok = ok && cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin) == cudaSuccess;
+  };
+  set(gemm_tc_kernel<1, 0>); set(gemm_tc_kernel<1, 1>); set(gemm_tc_kernel<1, 2>);
+  set(gemm_tc_kernel<2, 0>); set(gemm_tc_kernel<2, 1>); set(gemm_tc_kernel<2, 2>);
+  if (!ok) return set_error("cudaFuncSetAttribute(max dynamic smem) failed for gemm_tc_kernel");
   return 0;
 }
 
@@ -517,7 +681,7 @@ static int max_pairs() {
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, gemm_tc_kernel<2>, &cfg) != cudaSuccess || n <= 0) {
+    if (cudaOccupancyMaxActiveClusters(&n, gemm_tc_kernel<2, 0>, &cfg) != cudaSuccess || n <= 0) {
       cudaGetLastError();
       n = g_num_sms / 2;
     }
@@ -623,6 +787,12 @@ extern "C" int bb_gemm_bf16(const bb_gemm_args* a, void* stream_) {
       fg = (e_ && e_[0] == '1') ? 1 : 0;
     }
     p.fast_gelu = fg;
+    static int st = -1;
+    if (st < 0) {
+      const char* e_ = getenv("BB_GEMM_STAGED");
+      st = (e_ && e_[0] == '0') ? 0 : 1;
+    }
+    p.staged = st;
   }
   if (p.epi_mul && !p.aux_in) return set_error("bb_gemm_bf16: epi_mul needs aux_in");
   // vector epilogue only when every row segment of 16 outputs is 16-byte aligned (for bf16: 8 elements)
@@ -637,7 +807,7 @@ extern "C" int bb_gemm_bf16(const bb_gemm_args* a, void* stream_) {
   }
 
   const int stage_bytes = A_STAGE_BYTES + (bn / ctas) * BLOCK_K * 2;
-  int stages = (g_smem_optin - 1024 - 512 - 2048) / stage_bytes;
+  int stages = (g_smem_optin - 1024 - 512 - 2048 - STAGE_BYTES) / stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   {
     static int env_stages = -1;  // BB_GEMM_STAGES: pipeline-depth experiments only
@@ -649,7 +819,7 @@ extern "C" int bb_gemm_bf16(const bb_gemm_args* a, void* stream_) {
   }
   if (stages < 2) return set_error("bb_gemm_bf16: not enough shared memory for 2 stages");
   p.stages = stages;
-  const size_t smem_bytes = (size_t)stages * stage_bytes + 1024 + 512 + 2048;
+  const size_t smem_bytes = (size_t)stages * stage_bytes + 1024 + 512 + 2048 + STAGE_BYTES;
 
   CUtensorMap ta, tb;
   int e;
@@ -677,8 +847,22 @@ extern "C" int bb_gemm_bf16(const bb_gemm_args* a, void* stream_) {
     rec->dims[4] = p.a_mn; rec->dims[5] = p.b_mn;
     cudaEventRecord(rec->e0, stream);
   }
-  if (ctas == 2) bb::launch_pdl_cluster(gemm_tc_kernel<2>, grid, NUM_THREADS, smem_bytes, stream, 2, ta, tb, p, (int)total);
-  else bb::launch_pdl(gemm_tc_kernel<1>, grid, NUM_THREADS, smem_bytes, stream, ta, tb, p, (int)total);
+  // epilogue variant (BB_GEMM_EPI=0 forces the generic one, for A/B runs)
+  static int epi_mode = -1;
+  if (epi_mode < 0) {
+    const char* e_ = getenv("BB_GEMM_EPI");
+    epi_mode = (e_ && e_[0] == '0') ? 0 : 1;
+  }
+  int epi = 0;
+  const bool featureless = !p.act && !p.aux_out && !p.epi_mul && !p.add_in && !p.drop_thresh;
+  if (epi_mode && featureless) epi = p.atomic ? (p.bias ? 0 : 2) : 1;
+  auto go = [&](auto k1, auto k2) {
+    if (ctas == 2) bb::launch_pdl_cluster(k2, grid, NUM_THREADS, smem_bytes, stream, 2, ta, tb, p, (int)total);
+    else bb::launch_pdl(k1, grid, NUM_THREADS, smem_bytes, stream, ta, tb, p, (int)total);
+  };
+  if (epi == 1) go(gemm_tc_kernel<1, 1>, gemm_tc_kernel<2, 1>);
+  else if (epi == 2) go(gemm_tc_kernel<1, 2>, gemm_tc_kernel<2, 2>);
+  else go(gemm_tc_kernel<1, 0>, gemm_tc_kernel<2, 0>);
   if (rec) cudaEventRecord(rec->e1, stream);
   count_launch();
   return check_launch("gemm_tc_kernel");
