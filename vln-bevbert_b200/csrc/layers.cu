@@ -84,7 +84,6 @@ static AttnLayout attn_layout(const bb_attn_desc* d) {
 }
 
 static inline char* at(void* base, int64_t off) { return reinterpret_cast<char*>(base) + off; }
-static inline const char* at(const void* base, int64_t off) { return reinterpret_cast<const char*>(base) + off; }
 
 // y = epi(x W^T + b)
 static int lin_fwd(const void* x, const void* w, void* out, int64_t M, int N, int K, const float* bias, int act,
@@ -182,7 +181,7 @@ static int attn_core_bwd(const bb_attn_desc* d, const AttnLayout& L, const void*
   if (flash_on(d)) {
     bb_flash_args f;
     memset(&f, 0, sizeof(f));
-    f.q = q; f.k = k; f.v = v; f.o = const_cast<char*>(at(static_cast<const void*>(d->ws), L.ctx));
+    f.q = q; f.k = k; f.v = v; f.o = at(d->ws, L.ctx);   // the saved context (read-only here)
     f.q_bs = (int64_t)nq * ldq; f.k_bs = (int64_t)nk * ldk; f.v_bs = (int64_t)nk * ldv; f.o_bs = (int64_t)nq * HD;
     f.ldq = ldq; f.ldk = ldk; f.ldv = ldv; f.ldo = HD;
     f.B = B; f.H = H; f.nq = nq; f.nk = nk; f.dh = dh; f.alpha = 1.0f / sqrtf((float)dh);
