@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 def _worker(rank, world, port, task, ret, mode="ddp"):
     sys.path.insert(0, os.path.dirname(HERE))
     sys.path.insert(0, HERE)
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), BEVBERT_CHECK_ARENA="1")
     torch.set_num_threads(2)
     import emu_kernels
     emu_kernels.install()

@@ -8,8 +8,12 @@ time per step on a path that is already launch-bound, while every rank runs the 
 (`data/loader.py:50-61` broadcasts the task id), so the set of parameters that received a gradient is identical
 on all ranks and one coalesced all-reduce suffices.
 """
+import os
+
 import torch
 import torch.distributed as dist
+
+_CHECK_LAYOUT = os.environ.get("BEVBERT_CHECK_ARENA") == "1"
 
 
 class FlatGradAllReduce:
@@ -36,6 +40,11 @@ class FlatGradAllReduce:
             return
         inv = 1.0 / self.world
         if arena is not None and blocks.ARENA.off > 0:
+            if _CHECK_LAYOUT:      # debug (BEVBERT_CHECK_ARENA=1): every rank must have carved the same number of floats
+                n = torch.tensor([blocks.ARENA.off, -blocks.ARENA.off], dtype=torch.int64, device=arena.device)
+                dist.all_reduce(n, op=dist.ReduceOp.MAX)
+                if int(n[0]) != -int(n[1]):
+                    raise RuntimeError("gradient arena layouts differ across ranks (%d..%d floats)" % (-int(n[1]), int(n[0])))
             base = arena.untyped_storage().data_ptr()
             rest = [g for g in grads if g.untyped_storage().data_ptr() != base]
             used = arena[:blocks.ARENA.off]
