@@ -309,6 +309,38 @@ int bb_pano_ws_bytes(const bb_pano_desc* d, int64_t* fwd_bytes, int64_t* bwd_byt
 int bb_pano_fwd(const bb_pano_desc* d, void* stream);
 int bb_pano_bwd(const bb_pano_desc* d, void* stream);
 
+
+/* ---------------------------------------------------------------------------------------------
+ * Multi-tensor optimizer step on a DEVICE table of tensors (csrc/optim.cu): one launch for all parameters.
+ * Replaces the per-tensor python loop of pretrain_src/optim/adamw.py:53-112 (AdamW.step: eps inside the sqrt
+ * denominator sum, bias-corrected step size, decoupled weight decay applied AFTER the Adam update) and
+ * torch.nn.utils.clip_grad_norm_ at pretrain_src/train_r2r.py:295-300.
+ * A tensor occupies ceil(n / bb_mt_chunk_elems()) consecutive chunks starting at chunk0; the table is sorted by
+ * chunk0 and chunk0 of entry 0 is 0.  step_size = lr * sqrt(1-beta2^t) / (1-beta1^t) (or lr when correct_bias is
+ * off), decay = lr * weight_decay, both per tensor because each parameter has its own step counter t.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct bb_mt_tensor {
+  float* p;        /* fp32 parameter (bb_adamw_step: updated in place; bb_mt_cast_bf16: source) */
+  const float* g;  /* fp32 gradient (bb_mt_sumsq, bb_adamw_step) */
+  float* m;        /* exp_avg */
+  float* v;        /* exp_avg_sq */
+  void* p16;       /* bf16 shadow of p, written after the update (may be NULL in bb_adamw_step) */
+  int64_t n;       /* elements */
+  float step_size;
+  float decay;
+  int64_t chunk0;
+} bb_mt_tensor;
+int bb_mt_chunk_elems(void);
+/* *out = sum over all tensors of sum(g^2)  (zeroed on the stream first; fp32 atomics across CTAs) */
+int bb_mt_sumsq(const bb_mt_tensor* table_dev, int ntensors, int64_t total_chunks, float* out, void* stream);
+/* g' = g * grad_scale * min(1, max_norm / (grad_scale*sqrt(*sumsq) + 1e-6))   (no clipping when sumsq == NULL or
+ * max_norm <= 0); m = b1 m + (1-b1) g'; v = b2 v + (1-b2) g'^2; p -= step_size * m / (sqrt(v) + eps); p -= decay * p;
+ * p16 = bf16(p).  No host synchronisation: the norm is read on the device. */
+int bb_adamw_step(const bb_mt_tensor* table_dev, int ntensors, int64_t total_chunks, float beta1, float beta2, float eps,
+                  const float* sumsq, float max_norm, float grad_scale, void* stream);
+/* p16 = bf16(p) for every table entry (refresh of the bf16 weight shadows in one launch). */
+int bb_mt_cast_bf16(const bb_mt_tensor* table_dev, int ntensors, int64_t total_chunks, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

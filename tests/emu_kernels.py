@@ -10,6 +10,27 @@ import math
 import torch
 
 F32 = torch.float32
+ACT = F32      # storage dtype of activations; set_act_dtype(torch.bfloat16) makes every emulated kernel round its
+               # outputs where the CUDA kernels store bf16 (precision studies / tolerance derivations on CPU)
+
+
+ROUND = None   # study mode (ACT = float64 container): the set of sites whose outputs are rounded to bf16; None = n/a
+
+
+def set_act_dtype(dt, round_sites=None):
+    """dt = torch.bfloat16: every activation is stored (rounded) as bf16, like the CUDA kernels.
+    dt = torch.float64 + round_sites: activations live in an exact container and only the named sites round to
+    bf16 (scripts/precision_study.py): gemm_in gemm_out gemm_dx ln_y ln_dx ln_dres flash_p flash_ds flash_o
+    flash_dqkv other."""
+    global ACT, ROUND
+    ACT = dt
+    ROUND = set(round_sites) if round_sites is not None else None
+
+
+def _a(t, site="other"):
+    if ROUND is not None and ACT == torch.float64:
+        return t.to(torch.bfloat16).to(ACT) if site in ROUND else t.to(F32).to(ACT)
+    return t.to(ACT)
 
 
 def _strided(base, shape, strides):
@@ -22,12 +43,15 @@ def gemm(a, b, out, M, N, K, lda, ldb, ldd, a_mn=False, b_mn=False, nb1=1, nb2=1
     assert drop[1] == 0, "emulation runs with dropout disabled"
     A = _strided(a, (nb2, nb1, M, K), (a_s[1], a_s[0], 1, lda) if a_mn else (a_s[1], a_s[0], lda, 1))
     Bm = _strided(b, (nb2, nb1, N, K), (b_s[1], b_s[0], 1, ldb) if b_mn else (b_s[1], b_s[0], ldb, 1))
+    if ROUND is not None and "gemm_in" in ROUND:
+        A, Bm = A.to(torch.bfloat16), Bm.to(torch.bfloat16)
     v = torch.matmul(A.to(F32), Bm.to(F32).transpose(-1, -2)) * alpha
     if bias is not None:
         v = v + bias[:N].to(F32)
     dshape, dstr = (nb2, nb1, M, N), (d_s[1], d_s[0], ldd, 1)
+    osite = "gemm_dx" if add_in is not None else "gemm_out"
     if aux_out is not None:
-        _strided(aux_out, dshape, dstr).copy_(v)
+        _strided(aux_out, dshape, dstr).copy_(_a(v, osite) if aux_out.dtype == ACT else v)
     if act == 1:
         v = v * 0.5 * (1.0 + torch.erf(v / math.sqrt(2.0)))
     elif act == 2:
@@ -44,12 +68,12 @@ def gemm(a, b, out, M, N, K, lda, ldb, ldd, a_mn=False, b_mn=False, nb1=1, nb2=1
     if accumulate or split_k > 1:
         D.add_(v)
     else:
-        D.copy_(v)
+        D.copy_(_a(v, osite) if out.dtype == ACT and out.dtype != F32 else v)
     return out
 
 
 def act_dtype():
-    return F32
+    return ACT
 
 
 def native_sublayers():
@@ -93,8 +117,8 @@ def _flash_probs(q, k, B, H, nq, nk, ldq, ldk, kmask, bias):
 def flash_fwd(q, k, v, B, H, nq, nk, ldq, ldk, ldv, kmask=None, bias=None, drop=(0, 0, 1.0)):
     assert drop[1] == 0, "emulation runs with dropout disabled"
     p = _flash_probs(q, k, B, H, nq, nk, ldq, ldk, kmask, bias)
-    o = torch.matmul(p, _heads(v, B, nk, H, ldv).to(F32))          # (B,H,nq,64)
-    return o.permute(0, 2, 1, 3).reshape(B, nq, H * 64).contiguous(), torch.zeros(B, H, nq, dtype=F32)
+    o = torch.matmul(_a(p, 'flash_p').to(F32), _heads(v, B, nk, H, ldv).to(F32))          # (B,H,nq,64); P feeds the MMA as ACT
+    return _a(o.permute(0, 2, 1, 3).reshape(B, nq, H * 64).contiguous(), 'flash_o'), torch.zeros(B, H, nq, dtype=F32)
 
 
 def flash_bwd(q, k, v, o, lse, dout, B, H, nq, nk, ldq, ldk, ldv, kmask=None, bias=None, drop=(0, 0, 1.0), dbias=None,
@@ -104,17 +128,19 @@ def flash_bwd(q, k, v, o, lse, dout, B, H, nq, nk, ldq, ldk, ldv, kmask=None, bi
     p = _flash_probs(q, k, B, H, nq, nk, ldq, ldk, kmask, bias)
     do = _heads(dout, B, nq, H, Hd).to(F32)
     dp = torch.matmul(do, _heads(v, B, nk, H, ldv).to(F32).transpose(-1, -2))
-    ds = p * (dp - (p * dp).sum(-1, keepdim=True))
+    dsum = (do * _heads(o, B, nq, H, Hd).to(F32)).sum(-1, keepdim=True)      # rowsum(dO o O), as the kernel does
+    ds = p * (dp - dsum)
     if dbias is not None:
         dbias.add_(ds.sum(1))
+    ds = _a(ds, 'flash_ds').to(F32)
     if out is None:
-        dq, dk, dv = torch.zeros(B, nq, Hd, dtype=F32), torch.zeros(B, nk, Hd, dtype=F32), torch.zeros(B, nk, Hd, dtype=F32)
+        dq, dk, dv = torch.zeros(B, nq, Hd, dtype=ACT), torch.zeros(B, nk, Hd, dtype=ACT), torch.zeros(B, nk, Hd, dtype=ACT)
         lddq = lddk = lddv = Hd
     else:
         dq, lddq, dk, lddk, dv, lddv = out
-    _heads(dv, B, nk, H, lddv).copy_(torch.matmul(p.transpose(-1, -2), do))
-    _heads(dq, B, nq, H, lddq).copy_(torch.matmul(ds, _heads(k, B, nk, H, ldk).to(F32)) * 0.125)
-    _heads(dk, B, nk, H, lddk).copy_(torch.matmul(ds.transpose(-1, -2), _heads(q, B, nq, H, ldq).to(F32)) * 0.125)
+    _heads(dv, B, nk, H, lddv).copy_(_a(torch.matmul(_a(p, 'flash_p').to(F32).transpose(-1, -2), do), 'flash_dqkv'))
+    _heads(dq, B, nq, H, lddq).copy_(_a(torch.matmul(ds, _heads(k, B, nk, H, ldk).to(F32)) * 0.125, 'flash_dqkv'))
+    _heads(dk, B, nk, H, lddk).copy_(_a(torch.matmul(ds.transpose(-1, -2), _heads(q, B, nq, H, ldq).to(F32)) * 0.125, 'flash_dqkv'))
     return dq, dk, dv
 
 
@@ -162,7 +188,7 @@ def bev_scatter_mean(feats, cell_idx, ncell, want_f32=True, want_bf16=True):
     out = torch.stack([R.scatter_mean(feats[i], cell_idx[i].long(), ncell) for i in range(feats.shape[0])], 0)
     ob = ~((out.max(-1)[0] == 0) & (out.min(-1)[0] == 0))
     cnt = torch.stack([torch.bincount(cell_idx[i][cell_idx[i] >= 0].long(), minlength=ncell) for i in range(feats.shape[0])], 0)
-    return (out if want_f32 else None), (out.clone() if want_bf16 else None), ob, cnt.to(torch.int32)
+    return (out if want_f32 else None), (_a(out) if want_bf16 else None), ob, cnt.to(torch.int32)
 
 
 def bev_scatter_sem(sems, cell_idx, ncell):
@@ -175,7 +201,7 @@ def bev_scatter_sem(sems, cell_idx, ncell):
 def cast_to_act(src, drop=(0, 0, 1.0), out=None):
     assert drop[1] == 0
     if out is None:
-        return src.to(F32).clone()
+        return _a(src.to(F32).clone())
     out.copy_(src)
     return out
 
@@ -196,7 +222,7 @@ def layernorm_fwd(x, residual, gamma, beta, eps, drop_in=(0, 0, 1.0), drop_out=(
     var = ((z - mean[:, None]) ** 2).mean(-1)
     rstd = 1.0 / torch.sqrt(var + eps)
     y = (z - mean[:, None]) * rstd[:, None] * gamma + beta
-    return y, (y.clone() if want_f32 else None), mean, rstd
+    return _a(y, 'ln_y'), (y.clone() if want_f32 else None), mean, rstd
 
 
 def layernorm_bwd(dy, x, residual, gamma, mean, rstd, drop_in=(0, 0, 1.0), drop_out=(0, 0, 1.0), want_dx=True,
@@ -214,7 +240,7 @@ def layernorm_bwd(dy, x, residual, gamma, mean, rstd, drop_in=(0, 0, 1.0), drop_
         dbeta.add_(d.sum(0))
     if dxsum is not None:
         dxsum.add_(dz.sum(0))
-    return (dz.clone() if want_dx else None), (dz.clone() if want_dres else None)
+    return ((dz.clone() if dx_f32 else _a(dz, 'ln_dx')) if want_dx else None), (_a(dz, 'ln_dres') if want_dres else None)
 
 
 def colsum(x, N, out=None):
@@ -232,15 +258,15 @@ def softmax_fwd(scores, kmask, bias, nbatch, H, nq, nk, ld, drop=(0, 0, 1.0)):
         s = s + kmask.view(nbatch, 1, 1, nk)
     if bias is not None:
         s = s + bias.view(nbatch, 1, nq, nk)
-    p = torch.zeros(nbatch, H, nq, ld, dtype=F32)
+    p = torch.zeros(nbatch, H, nq, ld, dtype=ACT)
     p[..., :nk] = torch.softmax(s, -1)
     return p, p
 
 
 def softmax_bwd(probs, dprobs, nbatch, H, nq, nk, ld, drop, out_scale, dbias=None):
-    p, g = probs[..., :nk], dprobs[..., :nk]
+    p, g = probs[..., :nk].to(F32), dprobs[..., :nk]
     d = p * (g - (p * g).sum(-1, keepdim=True))
-    ds = torch.zeros(nbatch, H, nq, ld, dtype=F32)
+    ds = torch.zeros(nbatch, H, nq, ld, dtype=ACT)
     ds[..., :nk] = d * out_scale
     if dbias is not None:
         dbias.add_(d.sum(1))
@@ -261,9 +287,9 @@ def embed_scatter_grad(ids, dz, L, padding_idx, dword, dpos, dtype0):
 
 
 def gather_rows(src, idx, H):
-    out = torch.zeros(idx.numel(), H, dtype=F32)
+    out = torch.zeros(idx.numel(), H, dtype=ACT)
     keep = idx >= 0
-    out[keep] = src.reshape(-1, H)[idx[keep]]
+    out[keep] = src.reshape(-1, H)[idx[keep]].to(ACT)
     return out
 
 
@@ -276,7 +302,7 @@ def scatter_add_rows(src, idx, H, out_f32):
 def _act_bwd(dy, aux, mode):
     x = aux.to(F32)
     if mode == 1:
-        return dy * (0.5 * (1.0 + torch.erf(x / math.sqrt(2.0))) + x * torch.exp(-0.5 * x * x) / math.sqrt(2 * math.pi))
+        return _a(dy.to(F32) * (0.5 * (1.0 + torch.erf(x / math.sqrt(2.0))) + x * torch.exp(-0.5 * x * x) / math.sqrt(2 * math.pi)))
     return torch.where(x > 0, dy, torch.zeros_like(dy))
 
 
@@ -291,38 +317,38 @@ def relu_bwd(dy, post):
 def add_rows(a, b=None, table=None, idx=None, vec=None):
     out = a.to(F32).clone()
     if b is not None:
-        out = out + b
+        out = out + b.to(F32)
     if table is not None:
         out = out + table[idx]
     if vec is not None:
         out = out + vec[None]
-    return out
+    return _a(out)
 
 
 def scale_rows_(x, g, rows, ld):
-    x.mul_(g[:, None])
+    x.copy_(x.to(F32) * g[:, None])
     return x
 
 
 def segment_wsum(src, seg_off, idx, w, nseg, H):
     out = torch.zeros(nseg, H, dtype=F32)
     seg = torch.repeat_interleave(torch.arange(nseg), (seg_off[1:] - seg_off[:-1]).long())
-    out.index_add_(0, seg, src[idx.long()] * w[:, None])
-    return out
+    out.index_add_(0, seg, src[idx.long()].to(F32) * w[:, None])
+    return _a(out)
 
 
 def segment_wsum_bwd(dout, seg_off, idx, w, nseg, H, dsrc_f32):
     seg = torch.repeat_interleave(torch.arange(nseg), (seg_off[1:] - seg_off[:-1]).long())
-    dsrc_f32.view(-1, H).index_add_(0, idx.long(), dout[seg] * w[:, None])
+    dsrc_f32.view(-1, H).index_add_(0, idx.long(), dout[seg].to(F32) * w[:, None])
     return dsrc_f32
 
 
 def add_act(a, b):
-    return a + b
+    return _a(a.to(F32) + b.to(F32))
 
 
 def axpy_f32_from_act(x, y):
-    y.add_(x)
+    y.add_(x.to(F32))
     return y
 
 
@@ -334,14 +360,21 @@ def softmax_xent(logits, labels, V, ld, want_grad=True):
     loss = torch.where(valid, lse - x.gather(1, lab[:, None])[:, 0], torch.zeros_like(lse))
     dl = None
     if want_grad:
-        dl = torch.zeros(logits.shape[0], ld, dtype=F32)
+        dl = torch.zeros(logits.shape[0], ld, dtype=ACT)
         g = torch.softmax(x, -1)
         g[torch.arange(x.shape[0]), lab] -= 1.0
         dl[:, :V] = g * valid[:, None]
     return loss, dl
 
 
-_NAMES = ["flash_fwd", "flash_bwd", "attn_scores_fwd", "attn_scores_bwd", "gemm_profile", "gemm_profile_records", "native_sublayers", "attn_desc", "ffn_desc", "pano_desc", "sublayer_ws_bytes", "sublayer_fwd", "sublayer_bwd", "gemm", "act_dtype", "drop_params", "launch_count", "reset_launch_count", "bev_lift_index",
+def _no_mt(*a, **k):
+    raise RuntimeError("multi-tensor optimizer kernels take raw device pointers and are not emulated")
+
+
+MtTable = mt_cast_bf16 = mt_sumsq = adamw_step = _no_mt
+
+
+_NAMES = ["MtTable", "mt_cast_bf16", "mt_sumsq", "adamw_step", "flash_fwd", "flash_bwd", "attn_scores_fwd", "attn_scores_bwd", "gemm_profile", "gemm_profile_records", "native_sublayers", "attn_desc", "ffn_desc", "pano_desc", "sublayer_ws_bytes", "sublayer_fwd", "sublayer_bwd", "gemm", "act_dtype", "drop_params", "launch_count", "reset_launch_count", "bev_lift_index",
           "bev_scatter_mean", "bev_scatter_sem", "cast_to_act", "cast_to_f32", "dropout_act", "layernorm_fwd",
           "layernorm_bwd", "colsum", "softmax_fwd", "softmax_bwd", "embed_sum", "embed_scatter_grad", "gather_rows",
           "scatter_add_rows", "gelu_bwd", "relu_bwd", "add_rows", "scale_rows_", "segment_wsum", "segment_wsum_bwd",

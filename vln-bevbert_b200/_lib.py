@@ -83,6 +83,12 @@ class PanoDesc(C.Structure):
                                   "db2", "dg1", "dbe1", "dg2", "dbe2")]
 
 
+class MtTensor(C.Structure):
+    """struct bb_mt_tensor (include/bevbert_b200.h): one row of a multi-tensor launch table (64 bytes)."""
+    _fields_ = [("p", c_void_p), ("g", c_void_p), ("m", c_void_p), ("v", c_void_p), ("p16", c_void_p), ("n", c_i64),
+                ("step_size", c_float), ("decay", c_float), ("chunk0", c_i64)]
+
+
 # name -> (restype, argtypes); mirrors include/bevbert_b200.h one to one
 _SIGNATURES = {
     "bb_last_error": (C.c_char_p, []),
@@ -137,6 +143,10 @@ _SIGNATURES = {
     "bb_pano_ws_bytes": (c_int, [C.POINTER(PanoDesc), C.POINTER(c_i64), C.POINTER(c_i64)]),
     "bb_pano_fwd": (c_int, [C.POINTER(PanoDesc), c_void_p]),
     "bb_pano_bwd": (c_int, [C.POINTER(PanoDesc), c_void_p]),
+    "bb_mt_chunk_elems": (c_int, []),
+    "bb_mt_sumsq": (c_int, [c_void_p, c_int, c_i64, c_void_p, c_void_p]),
+    "bb_adamw_step": (c_int, [c_void_p, c_int, c_i64, c_float, c_float, c_float, c_void_p, c_float, c_float, c_void_p]),
+    "bb_mt_cast_bf16": (c_int, [c_void_p, c_int, c_i64, c_void_p]),
     "bb_softmax_xent": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_i64, c_void_p, c_void_p, c_void_p, c_void_p]),
 }
 

@@ -33,7 +33,16 @@ class DropState:
             return NO_DROP
         self.n += 1
         th, sc = K.drop_params(p)
-        return (self.base + self.n, th, sc)
+        # the kernels hash (element index XOR seed): consecutive site numbers would give masks that are XOR-shifted
+        # copies of each other, so every site gets a fully mixed 64-bit seed (splitmix64 finaliser)
+        return (_mix64(self.base + self.n), th, sc)
+
+
+def _mix64(x):
+    x = (x + 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
+    x = ((x ^ (x >> 30)) * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
+    x = ((x ^ (x >> 27)) * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF
+    return x ^ (x >> 31)
 
 
 class Runtime:
@@ -44,64 +53,155 @@ class Runtime:
         self.ds = DropState()
         self.feat_p = 0.0     # feature dropout requested by the pre-training wrapper (pretrain_cmt.py:102-106)
         self.calls = 0
+        self._stream_id = None
 
     def begin(self, training: bool, seed=None, tag=None):
         self.calls += 1
-        self.ds = DropState(training, self.calls * 7919 + 17 if seed is None else seed)
+        if seed is None:
+            if self._stream_id is None:
+                # dropout stream = f(torch.manual_seed, data-parallel rank): ranks draw different masks, and
+                # re-seeding torch re-seeds the kernels' counter-based RNG
+                import os
+                self._stream_id = _mix64(torch.initial_seed() ^ (int(os.environ.get("RANK", "0")) << 48)) & 0xFFFFFF
+            seed = (self.calls * 7919 + 17) ^ self._stream_id
+        self.ds = DropState(training, seed)
         if training:
             ARENA.new_step(tag)
             SCRATCH.new_step(tag)
+            if not self.wc.managed:     # a foreign optimizer may have stepped since the last forward (see WeightCache)
+                self.wc.refresh_all()
         return self.ds
 
 
+class _Shadow:
+    __slots__ = ("params", "buf", "ver", "epoch", "plain", "vec")
+
+    def __init__(self, params, buf, plain, vec=False):
+        self.params, self.buf, self.plain, self.vec = params, buf, plain, vec
+        self.ver, self.epoch = None, -1
+
+
 class WeightCache:
-    """bf16 shadows of fp32 parameters, refreshed when a parameter's version counter changes
-    (i.e. once per optimizer step).  Several parameters can be stacked row-wise into one operand
-    (packed Q|K|V), and tiny matrices are zero-padded to the 8-element granularity TMA needs."""
+    """bf16 shadows of the fp32 parameters (the GEMM operands).  Several parameters can be stacked row-wise into one
+    operand (packed Q|K|V), and tiny matrices are zero-padded to the 8-element granularity TMA needs.
+
+    Freshness.  Optimizers update `p.data` in place, which does NOT bump `p._version` (neither torch's fused AdamW nor
+    the reference's `p.data.addcdiv_`, pretrain_src/optim/adamw.py:99,110), so versions alone cannot tell when a
+    shadow is out of date.  Every shadow therefore also carries the cache epoch at which it was written:
+      * `bevbert_b200.optim.AdamW` (`managed`) writes the bf16 shadow of every parameter it updates inside its own
+        update kernel and marks stale only the shadows it could not write (zero-padded tiny operands);
+      * with any other optimizer `Runtime.begin(training=True)` advances the epoch at the
+        start of every training forward, which re-casts all stacked / plain shadows in ONE multi-tensor launch
+        (`refresh_all`, ~1.1 GB of traffic = ~0.2 ms per step on this model);
+      * `p._version` is still compared, which covers `load_state_dict` / `copy_` in eval mode."""
 
     def __init__(self):
         self._c = {}
+        self.epoch = 0
+        self.managed = False       # True once an optimizer that maintains the shadows itself is attached
+        self._table = None         # cached (key-set signature, device table, chunks) of refresh_all
+
+    # ------------------------------------------------------------------ lookups
+    def _fresh(self, ent):
+        return ent.epoch == self.epoch and ent.ver == tuple(p._version for p in ent.params)
 
     def get(self, *params, pad_k: int = 0, pad_n: int = 0):
         key = tuple(p.data_ptr() for p in params) + (pad_k, pad_n)
-        ver = tuple(p._version for p in params)
         ent = self._c.get(key)
-        if ent is not None and ent[0] == ver:
-            return ent[1]
+        if ent is not None and self._fresh(ent):
+            return ent.buf
         with torch.no_grad():
-            if len(params) == 1 and not pad_k and not pad_n:
-                buf = K.cast_to_act(params[0].detach(), out=ent[1] if ent is not None else None)
-            else:
+            plain = not pad_k and not pad_n
+            if ent is None:
                 n = sum(p.shape[0] for p in params)
                 k = params[0].shape[1]
-                kk, nn = max(k, pad_k), max(n, pad_n)
-                if not pad_k and not pad_n:
-                    buf = ent[1] if ent is not None else torch.empty(n, k, dtype=K.act_dtype(), device=params[0].device)
-                    r = 0
-                    for p in params:
-                        K.cast_to_act(p.detach(), out=buf[r:r + p.shape[0]])
-                        r += p.shape[0]
-                else:  # tiny padded operands: plain copies
-                    buf = torch.zeros(nn, kk, dtype=K.act_dtype(), device=params[0].device)
-                    r = 0
-                    for p in params:
-                        buf[r:r + p.shape[0], :k] = p.detach().to(K.act_dtype())
-                        r += p.shape[0]
-        self._c[key] = (ver, buf)
-        return buf
+                shape = (n, k) if plain else (max(n, pad_n), max(k, pad_k))
+                buf = (torch.empty if plain else torch.zeros)(shape, dtype=K.act_dtype(), device=params[0].device)
+                ent = _Shadow(params, buf, plain)
+                self._c[key] = ent
+                self._table = None
+            self._cast(ent)
+        return ent.buf
+
+    def _cast(self, ent):
+        if ent.plain:
+            r = 0
+            for p in ent.params:
+                K.cast_to_act(p.detach(), out=ent.buf[r:r + p.shape[0]])
+                r += p.shape[0]
+        else:  # tiny padded operands: plain copies
+            k = ent.params[0].shape[1]
+            r = 0
+            for p in ent.params:
+                ent.buf[r:r + p.shape[0], :k] = p.detach().to(K.act_dtype())
+                r += p.shape[0]
+        ent.ver, ent.epoch = tuple(p._version for p in ent.params), self.epoch
 
     def vec(self, *params):
-        """fp32 concatenation of 1-D parameters (packed Q|K|V bias), cached like the weights."""
+        """fp32 concatenation of 1-D parameters (packed Q|K|V bias) WITHOUT a copy per step: on first use the
+        parameters' storage is re-homed into one contiguous buffer (`p.data` becomes a view of it), so the packed
+        vector is always current whatever updates the parameters.  `module.to()` / `.cuda()` replace `p.data` and
+        break the aliasing; that is detected and the parameters are re-homed again."""
         if len(params) == 1:
             return params[0].detach()
-        key = ("v",) + tuple(p.data_ptr() for p in params)
-        ver = tuple(p._version for p in params)
+        key = ("v",) + tuple(id(p) for p in params)
         ent = self._c.get(key)
-        if ent is not None and ent[0] == ver:
-            return ent[1]
-        buf = torch.cat([p.detach() for p in params])
-        self._c[key] = (ver, buf)
+        if ent is not None:
+            off, ok = 0, True
+            for p in params:
+                ok = ok and p.data_ptr() == ent.buf.data_ptr() + off * 4 and p.device == ent.buf.device
+                off += p.numel()
+            if ok:
+                return ent.buf
+        with torch.no_grad():
+            buf = torch.cat([p.detach().reshape(-1) for p in params])
+            off = 0
+            for p in params:
+                p.data = buf[off:off + p.numel()].view(p.shape)
+                off += p.numel()
+            self._c[key] = _Shadow(params, buf, False, vec=True)
         return buf
+
+    # ------------------------------------------------------------------ invalidation / bulk refresh
+    def invalidate(self):
+        """Every shadow is out of date (parameters changed behind the cache's back)."""
+        self.epoch += 1
+
+    def refresh_all(self):
+        """Advance the epoch and re-cast every plain / stacked bf16 shadow in ONE multi-tensor launch; padded and
+        fp32-vector entries (a handful of tiny tensors) are refreshed lazily by `get` / `vec`."""
+        self.epoch += 1
+        ents = [e for e in self._c.values() if e.plain and not e.vec and e.buf.dtype == torch.bfloat16]
+        if not ents or not ents[0].buf.is_cuda:
+            return
+        if self._table is None:
+            rows = []
+            for e in ents:
+                off = 0
+                for p in e.params:
+                    rows.append((p.data_ptr(), 0, 0, 0, e.buf.data_ptr() + off * 2, p.numel(), 0.0, 0.0))
+                    off += p.numel()
+            self._table = K.MtTable(rows, ents[0].buf.device)
+        K.mt_cast_bf16(self._table)
+        for e in ents:
+            e.ver, e.epoch = tuple(p._version for p in e.params), self.epoch
+
+    def shadow_slots(self):
+        """{param data_ptr: [(bf16 address of the parameter's slot, entry)]} over the plain / stacked shadows: where an
+        optimizer kernel can write the bf16 copy of a parameter it has just updated."""
+        out = {}
+        for e in self._c.values():
+            if not e.plain or e.vec or e.buf.dtype != torch.bfloat16:
+                continue
+            off = 0
+            for p in e.params:
+                out.setdefault(p.data_ptr(), []).append((e.buf.data_ptr() + off * 2, e))
+                off += p.numel()
+        return out
+
+    def entries_with(self, param_ptrs):
+        """bf16 shadow entries (plain and padded) that hold at least one of the given parameters."""
+        return [e for e in self._c.values() if not e.vec and any(p.data_ptr() in param_ptrs for p in e.params)]
 
 
 class _ZeroArena:

@@ -32,8 +32,6 @@ constexpr int TMEM_COLS = 512;
 constexpr int STAGE_ROW_BYTES = 144;                     // 128 B of a row + 16 B pad (conflict-free 16-byte accesses)
 constexpr int STAGE_WARP_BYTES = 16 * STAGE_ROW_BYTES;   // 16 rows per pass
 constexpr int STAGE_BYTES = 8 * STAGE_WARP_BYTES;        // 18 KB for the 8 epilogue warps
-constexpr int STAGE2_WARP_BYTES = 32 * STAGE_ROW_BYTES;  // experiment (EPI 3 / 4): all 32 rows of a warp at once
-constexpr int STAGE2_BYTES = 8 * STAGE2_WARP_BYTES;      // 36 KB
 
 struct GemmKParams {
   int M, N, K;
@@ -296,119 +294,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const int lt = (tile - tile0) / tile_step;
       if (p.trace && lt < 16 && warp == 2 && lane == 0) p.trace[((long long)blockIdx.x * 16 + lt) * 4 + 2] = gtimer();
       const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + acc * 256;
-      if constexpr (EPI == 3 || EPI == 4) {
-        // EXPERIMENT, off by default (BB_GEMM_GELU_STAGED=1), not yet measured faster: the GELU products on coalesced
-        // accesses.  EPI 3: y = gelu(alpha acc + bias) plus the pre-activation as second output (FFN1 forward);
-        // EPI 4: y = dropout(alpha acc * gelu'(aux) | relu'(aux)) (dX through the FFN activation).  A warp stages all
-        // of its 32 rows x 128 B; every 16-byte piece is written to shared memory as soon as it is computed (no packed
-        // row in registers: the first version spilled), the second output is a second sweep over the same accumulator
-        // registers, and the gelu' operand arrives through the same staging area and is transformed in place.
-        uint8_t* stg = sstage + (warp - 2) * STAGE2_WARP_BYTES;
-        const int tile_row0 = (t.m_tile * CTAS + rank) * BLOCK_M + quarter * 32;
-        const long long batch_off = (long long)t.b1 * p.d_s1 + (long long)t.b2 * p.d_s2;
-        const long long row_bytes = p.ldd * 2;
-        auto rows_out = [&](uint8_t* gbase) {        // staged 32 x 128 B -> global, 4 full lines per instruction
-          __syncwarp();
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const int rr = k * 4 + (lane >> 3), ch = lane & 7;
-            const int grow = tile_row0 + rr;
-            if (grow < p.M)
-              *reinterpret_cast<uint4*>(gbase + grow * row_bytes + ch * 16) =
-                  *reinterpret_cast<const uint4*>(stg + rr * STAGE_ROW_BYTES + ch * 16);
-          }
-          __syncwarp();
-        };
-        for (int c = half * 64; c < p.block_n; c += 128) {
-          const int col0 = n0 + c;
-          if (col0 >= p.N) break;   // warp-uniform
-          const long long goff = (batch_off + col0) * 2;
-          if (EPI == 4) {             // gelu' / relu' operand: global -> staging (coalesced), overlaps the TMEM loads
-            const uint8_t* abase = reinterpret_cast<const uint8_t*>(p.aux_in) + goff;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              const int rr = k * 4 + (lane >> 3), ch = lane & 7;
-              const int grow = tile_row0 + rr;
-              uint4 val = make_uint4(0, 0, 0, 0);
-              if (grow < p.M) val = __ldg(reinterpret_cast<const uint4*>(abase + grow * row_bytes + ch * 16));
-              *reinterpret_cast<uint4*>(stg + rr * STAGE_ROW_BYTES + ch * 16) = val;
-            }
-          }
-          uint32_t r[64];
-          {
-            uint32_t(&r0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&r[0]);
-            uint32_t(&r1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&r[32]);
-            tmem_ld32(taddr + c, r0);
-            tmem_ld32(taddr + c + 32, r1);
-            tmem_ld_wait32(r1);
-            tmem_ld_wait32(r0);
-          }
-          __syncwarp();               // (EPI 4) the operand rows are in place
-          uint8_t* mine = stg + lane * STAGE_ROW_BYTES;
-          const long long my_off = batch_off + (long long)row * p.ldd + col0;
-          auto pre8 = [&](int j, float (&v)[8]) {    // alpha * acc (+ bias) for columns 8j .. 8j+7 of the slab
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[8 * j + i]) * p.alpha;
-            if (EPI == 3 && add_bias) {
-              const float4 b0 = *reinterpret_cast<const float4*>(sbias + acc * 256 + c + 8 * j);
-              const float4 b1 = *reinterpret_cast<const float4*>(sbias + acc * 256 + c + 8 * j + 4);
-              v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-              v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-            }
-          };
-          auto put8 = [&](int j, const float (&v)[8]) {
-            __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
-            __nv_bfloat162 h2 = __floats2bfloat162_rn(v[4], v[5]), h3 = __floats2bfloat162_rn(v[6], v[7]);
-            *reinterpret_cast<uint4*>(mine + j * 16) =
-                make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
-                           *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
-          };
-          if (EPI == 3) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {           // sweep 1: pre-activation
-              float v[8];
-              pre8(j, v);
-              put8(j, v);
-            }
-            rows_out(reinterpret_cast<uint8_t*>(p.aux_out) + goff);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {           // sweep 2: activation
-              float v[8];
-              pre8(j, v);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] = p.fast_gelu ? gelu_fast(v[i]) : gelu_erf(v[i]);
-              put8(j, v);
-            }
-            rows_out(reinterpret_cast<uint8_t*>(p.D) + goff);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float v[8];
-              pre8(j, v);
-              const uint4 araw = *reinterpret_cast<const uint4*>(mine + j * 16);
-              const __nv_bfloat162* ap = reinterpret_cast<const __nv_bfloat162*>(&araw);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const float2 a2 = __bfloat1622float2(ap[i]);
-                if (p.epi_mul == 1) {
-                  v[2 * i] *= p.fast_gelu ? dgelu_fast(a2.x) : dgelu_erf(a2.x);
-                  v[2 * i + 1] *= p.fast_gelu ? dgelu_fast(a2.y) : dgelu_erf(a2.y);
-                } else {
-                  v[2 * i] = a2.x > 0.0f ? v[2 * i] : 0.0f;
-                  v[2 * i + 1] = a2.y > 0.0f ? v[2 * i + 1] : 0.0f;
-                }
-              }
-              if (p.drop_thresh != 0) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-                  v[i] = drop_keep(p.drop_seed, (uint64_t)(my_off + 8 * j + i), p.drop_thresh) ? v[i] * p.drop_scale : 0.0f;
-              }
-              put8(j, v);                            // in place: only this lane touches its own row
-            }
-            rows_out(reinterpret_cast<uint8_t*>(p.D) + goff);
-          }
-        }
-      } else if constexpr (EPI != 0) {
+      if constexpr (EPI != 0) {
         // Specialised epilogues: 32-column TMEM loads, the next one in flight while the current 32 columns are
         // scaled / biased / converted / stored.  Warp `half` takes every other 32-column chunk.
         auto emit = [&](const uint32_t* r, const int c) {   // 16 columns starting at tile column c
@@ -773,10 +659,8 @@ static int init_device_info() {
   auto set = [&](auto kernel) {
     ok = ok && cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin) == cudaSuccess;
   };
-  set(gemm_tc_kernel<1, 0>); set(gemm_tc_kernel<1, 1>); set(gemm_tc_kernel<1, 2>); set(gemm_tc_kernel<1, 3>);
-  set(gemm_tc_kernel<1, 4>);
-  set(gemm_tc_kernel<2, 0>); set(gemm_tc_kernel<2, 1>); set(gemm_tc_kernel<2, 2>); set(gemm_tc_kernel<2, 3>);
-  set(gemm_tc_kernel<2, 4>);
+  set(gemm_tc_kernel<1, 0>); set(gemm_tc_kernel<1, 1>); set(gemm_tc_kernel<1, 2>);
+  set(gemm_tc_kernel<2, 0>); set(gemm_tc_kernel<2, 1>); set(gemm_tc_kernel<2, 2>);
   if (!ok) return set_error("cudaFuncSetAttribute(max dynamic smem) failed for gemm_tc_kernel");
   return 0;
 }
@@ -922,22 +806,17 @@ extern "C" int bb_gemm_bf16(const bb_gemm_args* a, void* stream_) {
     p.vec_ok = ok ? 1 : 0;
   }
 
-  // epilogue variant (BB_GEMM_EPI=0 forces the generic one, for A/B runs; BB_GEMM_GELU_STAGED=1 enables the
-  // experimental coalesced GELU variants 3 / 4 for 64-column-aligned bf16 outputs)
-  static int epi_mode = -1, gelu_staged = 0;
-  if (epi_mode < 0) {
+  // epilogue variant (BB_GEMM_EPI=0 forces the generic one, for A/B runs).  A staged (coalesced) variant of the
+  // GELU / gelu' epilogues was measured in round 2 (profiles/r02_selftest_gelu_staged.log): correct but slower than
+  // the direct stores (perf_ffn1 448 vs 567 TFLOP/s) and removed.
+  static const int epi_mode = [] {
     const char* e_ = getenv("BB_GEMM_EPI");
-    epi_mode = (e_ && e_[0] == '0') ? 0 : 1;
-    const char* g_ = getenv("BB_GEMM_GELU_STAGED");
-    gelu_staged = (g_ && g_[0] == '1') ? 1 : 0;
-  }
+    return (e_ && e_[0] == '0') ? 0 : 1;
+  }();
   int epi = 0;
   const bool featureless = !p.act && !p.aux_out && !p.epi_mul && !p.add_in && !p.drop_thresh;
-  const bool aligned64 = gelu_staged && p.vec_ok && !p.out_f32 && !p.atomic && a->N % 64 == 0 && bn % 64 == 0;
   if (epi_mode && featureless) epi = p.atomic ? (p.bias ? 0 : 2) : 1;
-  else if (epi_mode && aligned64 && p.act == 1 && p.aux_out && !p.epi_mul && !p.add_in && !p.drop_thresh) epi = 3;
-  else if (epi_mode && aligned64 && !p.act && !p.aux_out && p.epi_mul && !p.add_in && !p.bias) epi = 4;
-  const int stage_reserve = (epi == 3 || epi == 4) ? STAGE2_BYTES : STAGE_BYTES;
+  const int stage_reserve = STAGE_BYTES;
 
   const int stage_bytes = A_STAGE_BYTES + (bn / ctas) * BLOCK_K * 2;
   int stages = (g_smem_optin - 1024 - 512 - 2048 - stage_reserve) / stage_bytes;
@@ -984,9 +863,7 @@ extern "C" int bb_gemm_bf16(const bb_gemm_args* a, void* stream_) {
     if (ctas == 2) bb::launch_pdl_cluster(k2, grid, NUM_THREADS, smem_bytes, stream, 2, ta, tb, p, (int)total);
     else bb::launch_pdl(k1, grid, NUM_THREADS, smem_bytes, stream, ta, tb, p, (int)total);
   };
-  if (epi == 3) go(gemm_tc_kernel<1, 3>, gemm_tc_kernel<2, 3>);
-  else if (epi == 4) go(gemm_tc_kernel<1, 4>, gemm_tc_kernel<2, 4>);
-  else if (epi == 1) go(gemm_tc_kernel<1, 1>, gemm_tc_kernel<2, 1>);
+  if (epi == 1) go(gemm_tc_kernel<1, 1>, gemm_tc_kernel<2, 1>);
   else if (epi == 2) go(gemm_tc_kernel<1, 2>, gemm_tc_kernel<2, 2>);
   else go(gemm_tc_kernel<1, 0>, gemm_tc_kernel<2, 0>);
   if (rec) cudaEventRecord(rec->e1, stream);

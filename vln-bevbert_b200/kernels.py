@@ -479,3 +479,47 @@ def softmax_xent(logits, labels, V, ld, want_grad=True):
     _lib.check(lib.bb_softmax_xent(logits.data_ptr(), labels.data_ptr(), rows, V, ld, loss.data_ptr(), 0, _p(dl),
                                    _stream()), "bb_softmax_xent")
     return loss, dl
+
+
+# ---------------------------------------------------------------------------------------------- multi-tensor
+class MtTable:
+    """Device copy of a `bb_mt_tensor` table (include/bevbert_b200.h): rows = (p, g, m, v, p16, n, step_size, decay);
+    chunk offsets are filled in here.  The host rows live in a pinned numpy-backed tensor so that per-step updates
+    of the gradient pointers / step sizes are one asynchronous copy."""
+
+    def __init__(self, rows, device):
+        import numpy as np
+        self.dt = np.dtype([("p", "<u8"), ("g", "<u8"), ("m", "<u8"), ("v", "<u8"), ("p16", "<u8"), ("n", "<i8"),
+                            ("step_size", "<f4"), ("decay", "<f4"), ("chunk0", "<i8")])
+        assert self.dt.itemsize == C.sizeof(_lib.MtTensor)
+        self.nt = len(rows)
+        self.host = torch.empty(max(self.nt, 1) * self.dt.itemsize, dtype=torch.uint8)
+        if torch.cuda.is_available():
+            self.host = self.host.pin_memory()
+        self.np = self.host.numpy().view(self.dt)
+        chunk = int(_lib.load().bb_mt_chunk_elems())
+        c0 = 0
+        for i, r in enumerate(rows):
+            self.np[i] = tuple(r) + (c0,)
+            c0 += (int(r[5]) + chunk - 1) // chunk
+        self.chunks = c0
+        self.dev = torch.empty(self.host.numel(), dtype=torch.uint8, device=device)
+        self.upload()
+
+    def upload(self):
+        self.dev.copy_(self.host, non_blocking=True)
+
+
+def mt_cast_bf16(table: MtTable):
+    _lib.check(_lib.load().bb_mt_cast_bf16(table.dev.data_ptr(), table.nt, table.chunks, _stream()), "bb_mt_cast_bf16")
+
+
+def mt_sumsq(table: MtTable, out):
+    _lib.check(_lib.load().bb_mt_sumsq(table.dev.data_ptr(), table.nt, table.chunks, out.data_ptr(), _stream()),
+               "bb_mt_sumsq")
+    return out
+
+
+def adamw_step(table: MtTable, beta1, beta2, eps, sumsq=None, max_norm=0.0, grad_scale=1.0):
+    _lib.check(_lib.load().bb_adamw_step(table.dev.data_ptr(), table.nt, table.chunks, beta1, beta2, eps, _p(sumsq),
+                                         max_norm, grad_scale, _stream()), "bb_adamw_step")

@@ -1,58 +1,178 @@
-"""AdamW driver for the step loop: the same `torch._fused_adamw_` multi-tensor kernel as
-`torch.optim.AdamW(fused=True)`, with the per-step Python bookkeeping removed.
+"""AdamW + global-norm gradient clipping as ONE multi-tensor update over all parameters (csrc/optim.cu), with the
+reference's semantics:
 
-torch's optimizer walks every parameter of every group on each step (state lookup, list building, grouping by device
-and dtype: ~1.2 ms of host time for the 430 parameters of this model), which matters on a path whose whole step takes
-~15 ms and is host-bound.  Here the parameter / state lists are cached per "gradient signature" (the set of parameters
-that received a gradient: one signature per pre-training task), so a step is two foreach calls.
+  * `pretrain_src/optim/adamw.py:53-112` -- per-parameter step counter (a parameter without a gradient is skipped
+    entirely: no moment update, no decay, no step), m / v updates, `denom = sqrt(v) + eps` (eps OUTSIDE the sqrt,
+    default 1e-6), bias-corrected step size `lr * sqrt(1 - b2^t) / (1 - b1^t)` when `correct_bias`, and the decoupled
+    weight decay applied AFTER the Adam update on the updated value (`p -= lr * wd * p`);
+  * `pretrain_src/optim/misc.py:12-37` -- two parameter groups, no decay for bias / LayerNorm parameters
+    (`build_param_groups`);
+  * `pretrain_src/train_r2r.py:295-300` -- `clip_grad_norm_(model.parameters(), grad_norm)`: every gradient is scaled by
+    `min(1, max_norm / (||g||_2 + 1e-6))`; the norm is reduced and consumed on the device (no host sync) and returned
+    as a 0-d tensor for logging.
 
-Semantics follow torch.optim.AdamW: decoupled weight decay, bias correction from a per-parameter step counter,
-parameters without a gradient are skipped entirely (no decay, no moment update), state created lazily as zeros.
-The optimizer of the reference (pretrain_src/optim/) is out of scope; this is bench / training-loop plumbing.
+The same kernel writes the bf16 shadow of every updated weight (blocks.WeightCache), so no separate re-cast pass runs
+after the step.  This module only builds the launch tables; there is no PyTorch arithmetic on the parameters here.
 """
+import math
+
 import torch
 
+from . import kernels as K
 
-class FusedAdamW:
-    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2):
-        self.params = [p for p in params if p.requires_grad]
-        self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
-        self.state = {}       # index -> (exp_avg, exp_avg_sq, step)
-        self._lists = {}      # signature -> (params, exp_avgs, exp_avg_sqs, steps)
+NO_DECAY = ("bias", "LayerNorm.bias", "LayerNorm.weight")
 
-    def _state(self, i):
-        st = self.state.get(i)
-        if st is None:
-            p = self.params[i]
-            st = (torch.zeros_like(p, memory_format=torch.preserve_format),
-                  torch.zeros_like(p, memory_format=torch.preserve_format),
-                  torch.zeros((), dtype=torch.float32, device=p.device))
-            self.state[i] = st
-        return st
+
+def build_param_groups(model, weight_decay):
+    """pretrain_src/optim/misc.py:12-23."""
+    named = list(model.named_parameters())
+    return [{"params": [p for n, p in named if not any(nd in n for nd in NO_DECAY)], "weight_decay": weight_decay},
+            {"params": [p for n, p in named if any(nd in n for nd in NO_DECAY)], "weight_decay": 0.0}]
+
+
+class AdamW:
+    """`AdamW(params_or_groups, lr, betas, eps, weight_decay, correct_bias, max_grad_norm=None, runtime=None)`.
+    `runtime` (model.rt) lets the update kernel maintain the bf16 weight shadows; `param_groups` entries may carry
+    their own `lr` / `weight_decay` like torch optimizers (schedulers write `group["lr"]`)."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-6, weight_decay=0.0, correct_bias=True,
+                 max_grad_norm=None, runtime=None):
+        params = list(params)
+        if params and not isinstance(params[0], dict):
+            params = [{"params": params}]
+        self.param_groups = []
+        self.defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, correct_bias=correct_bias)
+        seen = set()
+        for g in params:
+            g = dict(g)
+            ps = []
+            for p in g["params"]:
+                if p.requires_grad and id(p) not in seen:
+                    seen.add(id(p))
+                    ps.append(p)
+            g["params"] = ps
+            for k, v in self.defaults.items():
+                g.setdefault(k, v)
+            self.param_groups.append(g)
+        self.max_grad_norm = max_grad_norm
+        self.rt = runtime
+        if runtime is not None:
+            runtime.wc.managed = True
+        self.flat = [(gi, p) for gi, g in enumerate(self.param_groups) for p in g["params"]]
+        self.steps = [0] * len(self.flat)
+        self.m = self.v = None
+        self._sumsq = None
+        self._tables = {}       # gradient signature -> (MtTable, [flat index], shadow entries fully covered)
+        self.grad_norm = None   # 0-d device tensor of the last step (pre-clip total norm), when clipping is on
+
+    # ------------------------------------------------------------------ state
+    def _init_state(self):
+        dev = self.flat[0][1].device
+        sizes = [(p.numel() + 3) // 4 * 4 for _, p in self.flat]
+        total = sum(sizes)
+        self._mbuf = torch.zeros(total, dtype=torch.float32, device=dev)
+        self._vbuf = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.m, self.v, off = [], [], 0
+        for (_, p), n in zip(self.flat, sizes):
+            self.m.append(self._mbuf[off:off + p.numel()])
+            self.v.append(self._vbuf[off:off + p.numel()])
+            off += n
+        self._sumsq = torch.zeros(1, dtype=torch.float32, device=dev)
+
+    def state_dict(self):
+        return {"steps": list(self.steps), "exp_avg": [m.clone() for m in (self.m or [])],
+                "exp_avg_sq": [v.clone() for v in (self.v or [])]}
+
+    def load_state_dict(self, sd):
+        if self.m is None:
+            self._init_state()
+        self.steps = list(sd["steps"])
+        for dst, src in zip(self.m, sd["exp_avg"]):
+            dst.copy_(src.reshape(-1))
+        for dst, src in zip(self.v, sd["exp_avg_sq"]):
+            dst.copy_(src.reshape(-1))
+
+    # ------------------------------------------------------------------ step
+    def _table(self, sig):
+        ent = self._tables.get(sig)
+        wc = self.rt.wc if self.rt is not None else None
+        if ent is not None and (wc is None or ent[3] == len(wc._c)):
+            return ent
+        slots = wc.shadow_slots() if wc is not None else {}
+        rows, written = [], set()
+        for i in sig:
+            p = self.flat[i][1]
+            sl = slots.get(p.data_ptr(), [])
+            p16 = sl[0][0] if sl else 0     # the update kernel writes ONE bf16 copy per parameter
+            rows.append((p.data_ptr(), 0, self.m[i].data_ptr(), self.v[i].data_ptr(), p16, p.numel(), 0.0, 0.0))
+            if sl:
+                written.add((p.data_ptr(), id(sl[0][1])))
+        # shadows that hold an updated parameter the kernel does not write (zero-padded tiny operands, a second shadow
+        # of the same parameter): marked stale after the step, WeightCache.get re-casts them
+        stale = []
+        if wc is not None:
+            ptrs = {self.flat[i][1].data_ptr() for i in sig}
+            for e in wc.entries_with(ptrs):
+                if any(q.data_ptr() in ptrs and (q.data_ptr(), id(e)) not in written for q in e.params):
+                    stale.append(e)
+        tab = K.MtTable(rows, self.flat[0][1].device)
+        ent = (tab, list(sig), stale, len(wc._c) if wc is not None else 0)
+        self._tables[sig] = ent
+        return ent
 
     @torch.no_grad()
-    def step(self, set_to_none=True):
-        sig = tuple(i for i, p in enumerate(self.params) if p.grad is not None)
+    def step(self, grad_scale=1.0, set_to_none=True):
+        sig = tuple(i for i, (_, p) in enumerate(self.flat) if p.grad is not None)
         if not sig:
-            return
-        lists = self._lists.get(sig)
-        if lists is None:
-            sts = [self._state(i) for i in sig]
-            lists = ([self.params[i] for i in sig], [s[0] for s in sts], [s[1] for s in sts], [s[2] for s in sts])
-            self._lists[sig] = lists
-        plist, m, v, steps = lists
-        grads = [p.grad for p in plist]
-        torch._foreach_add_(steps, 1)
-        torch._fused_adamw_(plist, grads, m, v, [], steps, lr=self.lr, beta1=self.betas[0], beta2=self.betas[1],
-                            weight_decay=self.weight_decay, eps=self.eps, amsgrad=False, maximize=False)
+            return None
+        if self.m is None:
+            self._init_state()
+        tab, idx, stale, _ = self._table(sig)
+        rows = tab.np
+        for r, i in enumerate(idx):
+            gi, p = self.flat[i]
+            g = p.grad
+            if g.dtype != torch.float32 or not g.is_contiguous():
+                g = p.grad = g.float().contiguous()
+            grp = self.param_groups[gi]
+            self.steps[i] += 1
+            t = self.steps[i]
+            lr = grp["lr"]
+            b1, b2 = grp["betas"]
+            ss = lr * math.sqrt(1.0 - b2 ** t) / (1.0 - b1 ** t) if grp["correct_bias"] else lr
+            if rows["p"][r] != p.data_ptr():      # storage moved (module.to(), bias re-homing): rebuild the table
+                self._tables.pop(sig, None)
+                self.steps = [st - (1 if j in idx[:r + 1] else 0) for j, st in enumerate(self.steps)]
+                return self.step(grad_scale, set_to_none)
+            rows["g"][r] = g.data_ptr()
+            rows["step_size"][r] = ss
+            rows["decay"][r] = lr * grp["weight_decay"]
+        tab.upload()
+        b1, b2 = self.param_groups[0]["betas"]
+        eps = self.param_groups[0]["eps"]
+        clip = self.max_grad_norm is not None and self.max_grad_norm > 0
+        if clip:
+            K.mt_sumsq(tab, self._sumsq)
+            self.grad_norm = self._sumsq
+        K.adamw_step(tab, b1, b2, eps, self._sumsq if clip else None, float(self.max_grad_norm or 0.0), grad_scale)
+        for e in stale:
+            e.epoch = -1
         if set_to_none:
-            for p in plist:
-                p.grad = None
+            for i in idx:
+                self.flat[i][1].grad = None
+        return self.grad_norm
+
+    def total_grad_norm(self):
+        """sqrt of the device-side sum of squares of the last clipped step (0-d tensor, no sync)."""
+        return None if self.grad_norm is None else self.grad_norm.sqrt()
 
     def zero_grad(self, set_to_none=True):
-        for p in self.params:
+        for _, p in self.flat:
             if p.grad is not None:
                 if set_to_none:
                     p.grad = None
                 else:
                     p.grad.zero_()
+
+
+FusedAdamW = AdamW   # round-1 name
