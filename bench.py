@@ -201,9 +201,12 @@ def run_ours(args, rank, world, local_rank):
         direct_param_grads(True)    # blocks assign p.grad themselves (no per-parameter AccumulateGrad nodes)
     if args.torch_optim:
         opt = torch.optim.AdamW(model.parameters(), lr=5e-5, weight_decay=0.01, fused=True)
-    else:   # same torch._fused_adamw_ kernel, parameter lists cached per task (bevbert_b200/optim.py)
-        from bevbert_b200.optim import FusedAdamW
-        opt = FusedAdamW(model.parameters(), lr=5e-5, weight_decay=0.01)
+    else:   # own multi-tensor AdamW + grad-norm clip kernel with the reference's update rule and hyper-parameters
+        #         (optim/adamw.py:53-112, train_r2r.py:298 grad_norm 5.0, optim/misc.py no-decay groups); it also writes
+        #         the bf16 weight shadows the next forward reads
+        from bevbert_b200.optim import AdamW, build_param_groups
+        opt = AdamW(build_param_groups(model, 0.01), lr=5e-5, betas=(0.9, 0.98), eps=1e-6, max_grad_norm=5.0,
+                    runtime=model.rt)
     Bs = args.batch
     scfg = synth.SynthConfig(batch_size=Bs)
     from bevbert_b200.model.ops import prepare_batch
@@ -418,7 +421,7 @@ def main():
     ap.add_argument("--batch", type=int, default=32, help="samples per GPU per step")
     ap.add_argument("--ref-batch", type=int, default=2, help="batch of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--torch-optim", action="store_true", help="torch.optim.AdamW(fused=True) instead of optim.FusedAdamW")
+    ap.add_argument("--torch-optim", action="store_true", help="torch.optim.AdamW(fused=True) instead of bevbert_b200.optim.AdamW")
     ap.add_argument("--wire", choices=("bf16", "fp32"), default="bf16",
                     help="host dtype of the large feature tensors in the end-to-end leg")
     ap.add_argument("--ddp", action="store_true", help="wrap with torch DDP instead of the flat gradient all-reduce")

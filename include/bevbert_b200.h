@@ -236,6 +236,13 @@ typedef struct bb_flash_args {
   float* dbias;
 } bb_flash_args;
 int bb_flash_fwd(const bb_flash_args* args, void* stream);
+/* Which core serves bb_flash_fwd / bb_flash_bwd: 0 = always the warp-level mma.sync kernels (csrc/attn_flash.cu),
+ * 1 (default, or env BB_ATTN_TC) = the tcgen05 / TMA kernels (csrc/attn_tc.cu) when nk >= 64 and bias == NULL,
+ * 2 = the tcgen05 kernels whenever they support the call (any nk; tests).  Returns the previous mode. */
+int bb_set_attn_tc(int mode);
+/* Debug: when device_buf is not NULL the tcgen05 forward kernel writes 8 %globaltimer stamps per CTA (first 256 CTAs):
+ * [0] start, [1] key mask staged, [2] S ready, [3] row max done, [4] P written, [5] O ready, [6] rows stored. */
+int bb_attn_tc_trace(long long* device_buf);
 int bb_flash_bwd(const bb_flash_args* args, void* stream);
 
 /* ---------------------------------------------------------------------------------------------

@@ -550,3 +550,47 @@ def test_native_pano_layer_equals_python_composition(K, monkeypatch):
     assert torch.equal(outs[True][0], outs[False][0]) and torch.equal(outs[True][1], outs[False][1])
     for a, b in zip(outs[True][2], outs[False][2]):
         assert rel_l2(a, b) < 1e-4
+
+
+@pytest.mark.parametrize("nq,nk,cross,mode", [(441, 441, False, 1), (441, 80, True, 1), (80, 441, True, 1), (80, 80, False, 1),
+                                              (130, 200, True, 1), (64, 128, True, 1), (100, 512, True, 1),
+                                              (512, 441, True, 1), (300, 600, True, 1), (36, 36, False, 2), (23, 80, True, 2),
+                                              (5, 7, True, 2)])
+def test_tcgen05_attention_forward_matches_fp32_and_mma_sync_paths(K, nq, nk, cross, mode):
+    """csrc/attn_tc.cu (tcgen05 + TMA, S in TMEM) vs fp32 torch attention and vs the mma.sync kernel (same LSE, same
+    dropout decisions): key masks (-10000 / -inf, a fully masked sample), ragged tails, 1..3 super-blocks."""
+    B, H, Hd = 3, 12, 768
+    if not cross:
+        qkv = rnd(B * nq, 3 * Hd, scale=0.8).cuda()
+        q, k, v, ldq, ldk, ldv = qkv, qkv[:, Hd:], qkv[:, 2 * Hd:], 3 * Hd, 3 * Hd, 3 * Hd
+    else:
+        q = rnd(B * nq, Hd, scale=0.8).cuda()
+        kv = rnd(B * nk, 2 * Hd, scale=0.8, seed=1).cuda()
+        k, v, ldq, ldk, ldv = kv, kv[:, Hd:], Hd, 2 * Hd, 2 * Hd
+    kmask = torch.zeros(B, nk)
+    kmask[1, nk // 2:] = -10000.0
+    kmask[0, -3:] = float("-inf")
+    kmask[2, :] = float("-inf")                      # every key masked: zero output rows, lse = +inf
+    kmask = kmask.cuda()
+    prev = K.set_attn_tc(mode)
+    try:
+        o, lse = K.flash_fwd(q, k, v, B, H, nq, nk, ldq, ldk, ldv, kmask, None)
+        o2, _ = K.flash_fwd(q, k, v, B, H, nq, nk, ldq, ldk, ldv)
+        th, sc = K.drop_params(0.1)
+        od, lsed = K.flash_fwd(q, k, v, B, H, nq, nk, ldq, ldk, ldv, kmask, None, (4242, th, sc))
+        K.set_attn_tc(0)
+        o_ref, lse_ref = K.flash_fwd(q, k, v, B, H, nq, nk, ldq, ldk, ldv, kmask, None)
+        od_ref, _ = K.flash_fwd(q, k, v, B, H, nq, nk, ldq, ldk, ldv, kmask, None, (4242, th, sc))
+    finally:
+        K.set_attn_tc(prev)
+    ro, _, _ = _flash_ref(q, k, v, B, H, nq, nk, ldq, ldk, ldv, kmask, None)     # sample 2 of the reference is NaN
+    assert rel_l2(o[:2], ro[:2]) < 6e-3
+    assert float(o[2].float().abs().max()) == 0.0 and torch.isinf(lse[2]).all()
+    ro2, _, _ = _flash_ref(q, k, v, B, H, nq, nk, ldq, ldk, ldv, None, None)
+    assert rel_l2(o2, ro2) < 6e-3
+    assert torch.isfinite(o.float()).all()
+    fin = torch.isfinite(lse_ref)
+    assert torch.equal(fin, torch.isfinite(lse)) and (lse[fin] - lse_ref[fin]).abs().max() < 2e-3
+    assert rel_l2(o[:2], o_ref[:2]) < 4e-3 and float(o_ref[2].float().abs().max()) == 0.0
+    # identical dropout decisions: the dropped outputs agree as closely as the undropped ones
+    assert rel_l2(od[:2], od_ref[:2]) < 6e-3 and (lsed[fin] - lse_ref[fin]).abs().max() < 2e-3

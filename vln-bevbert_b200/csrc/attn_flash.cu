@@ -23,6 +23,7 @@
 #include <string.h>
 
 #include "../../include/bevbert_b200.h"
+#include "attn_tc.h"
 #include "common.h"
 #include "ptx.cuh"
 
@@ -604,6 +605,7 @@ extern "C" int bb_flash_fwd(const bb_flash_args* a, void* stream) {
   using namespace bb;
   fa::Params p;
   if (int e = fa::fill(p, a, false)) return e;
+  if (fat::fwd_supported(a)) return fat::launch_fwd(a, stream);   // tcgen05 / TMA core (attn_tc.cu)
   const dim3 grid((unsigned)((a->nq + fa::BM - 1) / fa::BM), (unsigned)a->H, (unsigned)a->B);
   launch_pdl(fa::flash_fwd_kernel, grid, dim3(fa::NT), 0, (cudaStream_t)stream, p);
   count_launch();

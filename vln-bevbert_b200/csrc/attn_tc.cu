@@ -1,0 +1,422 @@
+// Attention core on tcgen05 tensor cores, fed by TMA, for head dim 64 and >= 64 keys (forward).
+//
+//   O = dropout(softmax(alpha Q K^T + kmask)) V        per (sample, head), scores / probabilities never leave the SM
+//
+// One CTA owns 128 queries of one (sample, head):
+//   warp 0 (one elected lane)  TMA producer + MMA issuer:
+//        Q (128 x 64) and all K / V rows of a "super-block" of up to 448 keys arrive by cp.async.bulk.tensor (128-byte
+//        swizzle, zero fill past the last row); S = Q K^T is one or two tcgen05.mma groups (M 128, N <= 256, 4 k-steps)
+//        into TMEM columns [64, 64 + keys); O += P V is issued per 64-key block as soon as the softmax warps publish it.
+//   warps 1..8 (256 threads)   softmax + epilogue: thread = (query row, key half).  Rows are TMEM lanes, so a thread
+//        reads its own score row with tcgen05.ld (32 columns per instruction), no shuffles:  pass 1 row maximum,
+//        pass 2 p = 2^(s - max), row sum, dropout, bf16 P written to shared memory in the K-major 128B-swizzled layout
+//        the second MMA consumes as its A operand (V is its MN-major B operand straight from the TMA tile).
+//        Finally O (TMEM columns [0, 64)) is normalised by the row sum and stored as bf16, and the row log-sum-exp is
+//        saved for backward.
+// The whole key range of a super-block is in TMEM at once (441 BEV cells -> 448 columns), so there is no online-softmax
+// rescaling of O; longer rows (RxR, 512 keys) run as several super-blocks merged in registers.
+//
+// TMEM: 512 columns = O (64) + S (448).  Shared memory: Q 16 KB + K 56 KB + V 56 KB + P 2 x 16 KB.
+//
+// Reference semantics: BertSelfAttention / BertOutAttention (vilmodel.py:103-154, 325-363); same dropout function and
+// log2-domain LSE as csrc/attn_flash.cu (mma.sync path, kept for < 64 keys and for the graph-bias case).
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../../include/bevbert_b200.h"
+#include "attn_tc.h"
+#include "common.h"
+#include "ptx.cuh"
+
+namespace bb {
+namespace fat {
+
+typedef __nv_bfloat16 bf16;
+constexpr int BM = 128;
+constexpr int KB = 64;           // keys per K / V / P block
+constexpr int MAX_SBK = 448;     // keys per super-block (S columns in TMEM)
+constexpr int NT = 288;          // warp 0 + 8 softmax warps
+constexpr int O_COL = 0, S_COL = 64;
+constexpr int Q_BYTES = BM * 128, BLK_BYTES = KB * 128, P_BYTES = BM * 128;
+constexpr float LOG2E = 1.4426950408889634f;
+
+struct FwdParams {
+  bf16* out;
+  int64_t o_bs;
+  int ldo;
+  float* lse;
+  const float* kmask;
+  int B, H, nq, nk;
+  int nsb, sbk;       // super-blocks, keys per super-block (multiple of 64)
+  float a2;           // alpha * log2(e)
+  uint64_t seed;
+  uint32_t thresh;
+  float scale;
+  int tmem_cols;
+  long long* trace;   // debug: 8 %globaltimer stamps per CTA (first 256 CTAs) or null
+};
+__device__ __forceinline__ long long gtimer() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define FAT_STAMP(i)                                                                                       \
+  do {                                                                                                     \
+    if (p.trace && st == 0 && cta_lin < 256) p.trace[cta_lin * 8 + (i)] = gtimer();                        \
+  } while (0)
+
+__device__ __forceinline__ float ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+// same decisions as csrc/attn_flash.cu: one hash per (sample, head, query) row, one mix per PAIR of adjacent keys
+__device__ __forceinline__ uint32_t mix_pair(uint32_t rowhash, uint32_t pair) {
+  uint32_t x = rowhash ^ (pair * 0x9E3779B1u);
+  x ^= x >> 15;
+  x *= 0x2C1B3C6Du;
+  x ^= x >> 12;
+  x *= 0x297A2D39u;
+  x ^= x >> 15;
+  return x;
+}
+__device__ __forceinline__ void named_sync_256() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+__global__ void __launch_bounds__(NT, 1)
+attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk,
+                   const __grid_constant__ CUtensorMap tv, const FwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int nkb_max = p.sbk / KB;
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + Q_BYTES;
+  uint8_t* sV = sK + nkb_max * BLK_BYTES;
+  uint8_t* sP = sV + nkb_max * BLK_BYTES;
+  float* skm = reinterpret_cast<float*>(sP + 2 * P_BYTES);       // [sbk] log2-domain key mask
+  float* smax = skm + p.sbk;                                     // [2][128]
+  float* ssum = smax + 2 * BM;                                   // [2][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ssum + 2 * BM);
+  uint64_t* q_full = bars + 0;
+  uint64_t* k_full = bars + 1;
+  uint64_t* v_full = bars + 2;
+  uint64_t* s_full = bars + 3;
+  uint64_t* o_full = bars + 4;
+  uint64_t* o_read = bars + 5;
+  uint64_t* p_full = bars + 6;    // [2]
+  uint64_t* p_empty = bars + 8;   // [2]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 10);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * BM, h = blockIdx.y, b = blockIdx.z;
+  const int cta_lin = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+  if (p.trace && threadIdx.x == 32 && cta_lin < 256) p.trace[cta_lin * 8 + 0] = gtimer();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tq);
+      tma_prefetch_desc(&tk);
+      tma_prefetch_desc(&tv);
+      mbar_init(q_full, 1);
+      mbar_init(k_full, 1);
+      mbar_init(v_full, 1);
+      mbar_init(s_full, 1);
+      mbar_init(o_full, 1);
+      mbar_init(o_read, 256);
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&p_full[i], 128);
+        mbar_init(&p_empty[i], 1);
+      }
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_ptr_smem, (uint32_t)p.tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();
+  pdl_trigger();
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer + MMA issuer
+    if (lane == 0) {
+      mbar_expect_tx(q_full, Q_BYTES);
+      tma_load_4d(sQ, &tq, q_full, 0, q0, h, b);
+      const uint32_t idesc_pv = umma_idesc_bf16(BM, 64, 0, 1);
+      uint32_t pf_phase[2] = {0, 0};
+      for (int sb = 0; sb < p.nsb; ++sb) {
+        const int key0 = sb * p.sbk;
+        const int nkeys = min(p.sbk, p.nk - key0);
+        const int nblk = (nkeys + KB - 1) / KB;
+        if (sb > 0) mbar_wait(o_read, (sb - 1) & 1);   // S and O of the previous super-block have been consumed
+        mbar_expect_tx(k_full, nblk * BLK_BYTES);
+        for (int j = 0; j < nblk; ++j) tma_load_4d(sK + j * BLK_BYTES, &tk, k_full, 0, key0 + j * KB, h, b);
+        mbar_expect_tx(v_full, nblk * BLK_BYTES);
+        for (int j = 0; j < nblk; ++j) tma_load_4d(sV + j * BLK_BYTES, &tv, v_full, 0, key0 + j * KB, h, b);
+        if (sb == 0) mbar_wait(q_full, 0);
+        mbar_wait(k_full, sb & 1);
+        tc_fence_after();
+        // S = Q K^T
+        const int n_eff = (nkeys + 31) & ~31;   // whole 32-column chunks are read back; K rows past nk are zero-filled
+        const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK);
+        for (int n0 = 0; n0 < n_eff; n0 += 256) {
+          const int nn = min(256, n_eff - n0);
+          const uint32_t idesc = umma_idesc_bf16(BM, nn, 0, 0);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16_ss(tmem_base + S_COL + n0, umma_smem_desc(aQ + k * 32, 16, 1024),
+                         umma_smem_desc(aK + n0 * 128 + k * 32, 16, 1024), idesc, k > 0 ? 1u : 0u);
+        }
+        umma_commit(s_full);
+        // O (+)= P V, one 64-key block at a time
+        mbar_wait(v_full, sb & 1);
+        const uint32_t aP = smem_u32(sP), aV = smem_u32(sV);
+        for (int j = 0; j < nblk; ++j) {
+          const int slot = j & 1;
+          mbar_wait(&p_full[slot], pf_phase[slot]);
+          pf_phase[slot] ^= 1;
+          tc_fence_after();
+          const int ksteps = (min(KB, nkeys - j * KB) + 15) >> 4;
+          for (int k = 0; k < ksteps; ++k)
+            umma_bf16_ss(tmem_base + O_COL, umma_smem_desc(aP + slot * P_BYTES + k * 32, 16, 1024),
+                         umma_smem_desc(aV + j * BLK_BYTES + k * 2048, 8192, 1024), idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
+          umma_commit(&p_empty[slot]);
+        }
+        umma_commit(o_full);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ softmax + epilogue (256 threads)
+    const int quarter = warp & 3;             // TMEM lane quarter this warp may access
+    const int hf = (warp - 1) >> 2;           // key half: blocks j = hf, hf + 2, ...
+    const int row = quarter * 32 + lane;      // query row in the tile = TMEM lane
+    const int st = threadIdx.x - 32;          // 0..255
+    const uint32_t trow = tmem_base + (uint32_t(quarter * 32) << 16);
+    const int64_t grow = ((int64_t)b * p.H + h) * p.nq + q0 + row;
+    const uint32_t rh = p.thresh ? rng_u32(p.seed, (uint64_t)grow) : 0u;
+    const uint32_t t16 = p.thresh >> 16;
+    uint8_t* prow = sP + hf * P_BYTES + (row >> 3) * 1024 + (row & 7) * 128;
+    const int sw = row & 7;
+    uint32_t pe_phase = 0;
+    float m_run = -INFINITY, l_run = 0.f;
+    float o_run[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) o_run[i] = 0.f;
+
+    for (int sb = 0; sb < p.nsb; ++sb) {
+      const int key0 = sb * p.sbk;
+      const int nkeys = min(p.sbk, p.nk - key0);
+      const int nblk = (nkeys + KB - 1) / KB;
+      // log2-domain additive key mask of this super-block (previous one fully consumed: o_read / s_full ordering)
+      for (int i = st; i < p.sbk; i += 256) {
+        const int col = key0 + i;
+        skm[i] = i < nkeys ? (p.kmask ? __ldg(p.kmask + (int64_t)b * p.nk + col) * LOG2E : 0.f) : -INFINITY;
+      }
+      named_sync_256();
+      FAT_STAMP(1);
+      mbar_wait(s_full, sb & 1);
+      tc_fence_after();
+      FAT_STAMP(2);
+      // ---- pass 1: row maximum over this thread's blocks
+      float mx = -INFINITY;
+      for (int j = hf; j < nblk; j += 2) {
+#pragma unroll
+        for (int c = 0; c < KB; c += 32) {
+          if (j * KB + c < nkeys) {
+            uint32_t r[32];
+            tmem_ld32(trow + S_COL + j * KB + c, r);
+            tmem_ld_wait32(r);
+            const float4* km4 = reinterpret_cast<const float4*>(skm + j * KB + c);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 km = km4[i];
+              mx = fmaxf(mx, fmaf(__uint_as_float(r[4 * i + 0]), p.a2, km.x));
+              mx = fmaxf(mx, fmaf(__uint_as_float(r[4 * i + 1]), p.a2, km.y));
+              mx = fmaxf(mx, fmaf(__uint_as_float(r[4 * i + 2]), p.a2, km.z));
+              mx = fmaxf(mx, fmaf(__uint_as_float(r[4 * i + 3]), p.a2, km.w));
+            }
+          }
+        }
+      }
+      smax[hf * BM + row] = mx;
+      named_sync_256();
+      FAT_STAMP(3);
+      const float m = fmaxf(smax[row], smax[BM + row]);
+      const float ms = m == -INFINITY ? 0.f : m;
+      // ---- pass 2: probabilities -> bf16 P blocks in shared memory (A operand of the PV product)
+      float lsum = 0.f;
+      for (int j = hf; j < nblk; j += 2) {
+        mbar_wait(&p_empty[hf], pe_phase ^ 1);
+#pragma unroll
+        for (int c = 0; c < KB; c += 32) {
+          uint32_t pk[16];
+          if (j * KB + c < nkeys) {
+            uint32_t r[32];
+            tmem_ld32(trow + S_COL + j * KB + c, r);
+            tmem_ld_wait32(r);
+            const float4* km4 = reinterpret_cast<const float4*>(skm + j * KB + c);
+            const uint32_t pair0 = (uint32_t)(key0 + j * KB + c) >> 1;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 km = km4[i];
+              float e0 = ex2f(fmaf(__uint_as_float(r[4 * i + 0]), p.a2, km.x) - ms);
+              float e1 = ex2f(fmaf(__uint_as_float(r[4 * i + 1]), p.a2, km.y) - ms);
+              float e2 = ex2f(fmaf(__uint_as_float(r[4 * i + 2]), p.a2, km.z) - ms);
+              float e3 = ex2f(fmaf(__uint_as_float(r[4 * i + 3]), p.a2, km.w) - ms);
+              lsum += (e0 + e1) + (e2 + e3);
+              if (p.thresh) {
+                const uint32_t x0 = mix_pair(rh, pair0 + 2 * i), x1 = mix_pair(rh, pair0 + 2 * i + 1);
+                e0 = (x0 & 0xFFFFu) >= t16 ? e0 * p.scale : 0.f;
+                e1 = (x0 >> 16) >= t16 ? e1 * p.scale : 0.f;
+                e2 = (x1 & 0xFFFFu) >= t16 ? e2 * p.scale : 0.f;
+                e3 = (x1 >> 16) >= t16 ? e3 * p.scale : 0.f;
+              }
+              pk[2 * i] = pack2(e0, e1);
+              pk[2 * i + 1] = pack2(e2, e3);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) pk[i] = 0u;
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {   // 16-byte chunk (c/8 + i) of this row, XOR-swizzled by the row (128B swizzle)
+            const int ch = (c >> 3) + i;
+            *reinterpret_cast<uint4*>(prow + ((ch ^ sw) << 4)) = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+          }
+        }
+        fence_proxy_async();          // generic-proxy stores -> visible to the tensor core's async-proxy reads
+        mbar_arrive(&p_full[hf]);
+        pe_phase ^= 1;
+      }
+      ssum[hf * BM + row] = lsum;
+      named_sync_256();
+      FAT_STAMP(4);
+      const float l = ssum[row] + ssum[BM + row];
+      // ---- O of this super-block: columns [32 hf, 32 hf + 32) of the row
+      mbar_wait(o_full, sb & 1);
+      tc_fence_after();
+      FAT_STAMP(5);
+      uint32_t r[32];
+      tmem_ld32(trow + O_COL + hf * 32, r);
+      tmem_ld_wait32(r);
+      const float m_new = fmaxf(m_run, m);
+      const float mb = m_new == -INFINITY ? 0.f : m_new;
+      const float c_run = ex2f(m_run - mb), c_sb = ex2f(m - mb);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) o_run[i] = o_run[i] * c_run + __uint_as_float(r[i]) * c_sb;
+      l_run = l_run * c_run + l * c_sb;
+      m_run = m_new;
+      if (sb + 1 < p.nsb) {
+        tc_fence_before();
+        mbar_arrive(o_read);
+      }
+    }
+    // ---- epilogue: normalise, store bf16 rows and the log2-domain log-sum-exp
+    if (q0 + row < p.nq) {
+      const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;
+      bf16* dst = p.out + (int64_t)b * p.o_bs + (int64_t)(q0 + row) * p.ldo + h * 64 + hf * 32;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        reinterpret_cast<uint4*>(dst)[i] = make_uint4(pack2(o_run[8 * i] * inv, o_run[8 * i + 1] * inv),
+                                                      pack2(o_run[8 * i + 2] * inv, o_run[8 * i + 3] * inv),
+                                                      pack2(o_run[8 * i + 4] * inv, o_run[8 * i + 5] * inv),
+                                                      pack2(o_run[8 * i + 6] * inv, o_run[8 * i + 7] * inv));
+      if (hf == 0 && p.lse) p.lse[grow] = l_run > 0.f ? m_run + log2f(l_run) : INFINITY;
+    }
+    FAT_STAMP(6);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
+static int g_smem_optin = 0;
+static int init_once() {
+  if (g_smem_optin) return 0;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return set_error("cudaGetDevice failed");
+  cudaDeviceGetAttribute(&g_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  if (cudaFuncSetAttribute(attn_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin) != cudaSuccess)
+    return set_error("cudaFuncSetAttribute failed for attn_tc_fwd_kernel");
+  return 0;
+}
+
+// BB_ATTN_TC: 0 = never, 1 (default) = when nk >= 64, 2 = whenever the kernel supports the call (tests)
+static long long* g_trace = nullptr;
+static int g_tc_mode = -1;
+int tc_mode() {
+  if (g_tc_mode < 0) {
+    const char* e = getenv("BB_ATTN_TC");
+    g_tc_mode = e ? atoi(e) : 1;
+  }
+  return g_tc_mode;
+}
+int set_tc_mode(int mode) {
+  const int prev = tc_mode();
+  g_tc_mode = mode;
+  return prev;
+}
+
+bool fwd_supported(const bb_flash_args* a) {
+  const int mode = tc_mode();
+  if (mode == 0 || a->dh != 64 || a->bias != nullptr) return false;
+  if (mode == 1 && a->nk < 64) return false;
+  const uintptr_t al = reinterpret_cast<uintptr_t>(a->q) | reinterpret_cast<uintptr_t>(a->k) |
+                       reinterpret_cast<uintptr_t>(a->v) | reinterpret_cast<uintptr_t>(a->o);
+  if (al & 15) return false;
+  if ((a->ldq | a->ldk | a->ldv | a->ldo) % 8) return false;
+  if ((a->q_bs | a->k_bs | a->v_bs | a->o_bs) % 8) return false;
+  return true;
+}
+
+int launch_fwd(const bb_flash_args* a, void* stream) {
+  if (int e = init_once()) return e;
+  FwdParams p;
+  memset(&p, 0, sizeof(p));
+  p.out = (bf16*)a->o; p.o_bs = a->o_bs; p.ldo = a->ldo; p.lse = a->lse; p.kmask = a->kmask;
+  p.B = a->B; p.H = a->H; p.nq = a->nq; p.nk = a->nk;
+  p.nsb = (a->nk + MAX_SBK - 1) / MAX_SBK;
+  p.sbk = (((a->nk + p.nsb - 1) / p.nsb) + KB - 1) / KB * KB;
+  p.nsb = (a->nk + p.sbk - 1) / p.sbk;
+  p.a2 = a->alpha * LOG2E;
+  p.seed = a->seed; p.thresh = a->thresh; p.scale = a->scale;
+  const int need = S_COL + p.sbk;
+  p.tmem_cols = need <= 128 ? 128 : (need <= 256 ? 256 : 512);
+  p.trace = g_trace;
+  CUtensorMap tq, tk, tv;
+  if (int e = make_tmap_bf16_4d(&tq, a->q, 64, a->nq, a->H, a->B, a->ldq, 64, a->q_bs, BM)) return e;
+  if (int e = make_tmap_bf16_4d(&tk, a->k, 64, a->nk, a->H, a->B, a->ldk, 64, a->k_bs, KB)) return e;
+  if (int e = make_tmap_bf16_4d(&tv, a->v, 64, a->nk, a->H, a->B, a->ldv, 64, a->v_bs, KB)) return e;
+  const int nkb = p.sbk / KB;
+  const size_t smem = 1024 + Q_BYTES + 2 * (size_t)nkb * BLK_BYTES + 2 * P_BYTES + (size_t)p.sbk * 4 + 4 * BM * 4 + 128;
+  if ((int)smem > g_smem_optin) return set_error("attn_tc_fwd: shared memory budget exceeded");
+  const dim3 grid((unsigned)((a->nq + BM - 1) / BM), (unsigned)a->H, (unsigned)a->B);
+  launch_pdl(attn_tc_fwd_kernel, grid, dim3(NT), smem, (cudaStream_t)stream, tq, tk, tv, p);
+  count_launch();
+  return check_launch("attn_tc_fwd_kernel");
+}
+
+}  // namespace fat
+}  // namespace bb
+
+extern "C" int bb_set_attn_tc(int mode) { return bb::fat::set_tc_mode(mode); }
+extern "C" int bb_attn_tc_trace(long long* device_buf) {
+  bb::fat::g_trace = device_buf;
+  return 0;
+}

@@ -11,6 +11,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <mutex>
+#include <unordered_map>
 #include <vector>
 #include <stdio.h>
 #include <stdlib.h>
@@ -606,18 +607,47 @@ static PFN_encodeTiled get_encode() {
 }
 
 // 4-D bf16 tensor map: dims (inner, rows, b1, b2) with element strides (1, ld, s1, s2); box (64, box_rows, 1, 1).
-static int make_map(CUtensorMap* map, const void* base, uint64_t inner, uint64_t rows, uint64_t nb1, uint64_t nb2,
-                    int64_t ld, int64_t s1, int64_t s2, uint32_t box_rows) {
+// Encoded maps are cached per (base, geometry): a training step re-creates the same ~600 maps every step (the caching
+// allocator hands back the same activation addresses), and cuTensorMapEncodeTiled is host work on a host-co-limited
+// path.  The map only depends on the key, so a stale entry can never be wrong; the cache is dropped when it grows.
+struct MapKey {
+  const void* base;
+  uint64_t inner, rows, nb1, nb2;
+  int64_t ld, s1, s2;
+  uint32_t box_rows;
+  bool operator==(const MapKey& o) const {
+    return base == o.base && inner == o.inner && rows == o.rows && nb1 == o.nb1 && nb2 == o.nb2 && ld == o.ld &&
+           s1 == o.s1 && s2 == o.s2 && box_rows == o.box_rows;
+  }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    uint64_t h = reinterpret_cast<uintptr_t>(k.base) * 0x9E3779B97F4A7C15ull;
+    auto mix = [&](uint64_t v) { h = (h ^ v) * 0xBF58476D1CE4E5B9ull; h ^= h >> 29; };
+    mix(k.inner); mix(k.rows); mix(k.nb1); mix(k.nb2); mix((uint64_t)k.ld); mix((uint64_t)k.s1); mix((uint64_t)k.s2);
+    mix(k.box_rows);
+    return (size_t)h;
+  }
+};
+int make_tmap_bf16_4d(CUtensorMap* map, const void* base, uint64_t inner, uint64_t rows, uint64_t nb1, uint64_t nb2,
+                      int64_t ld, int64_t s1, int64_t s2, uint32_t box_rows) {
   PFN_encodeTiled enc = get_encode();
   if (!enc) return set_error("cuTensorMapEncodeTiled entry point not available");
-  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return set_error("gemm operand base not 16-byte aligned");
-  if (ld % 8 != 0) return set_error("gemm operand leading dimension must be a multiple of 8 elements");
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return set_error("tensor-map operand base not 16-byte aligned");
+  if (ld % 8 != 0) return set_error("tensor-map operand leading dimension must be a multiple of 8 elements");
   // unused batch dims get a harmless 16-byte-multiple stride
   if (nb1 <= 1) s1 = ld * (int64_t)rows;
   if (nb2 <= 1) s2 = s1 * (int64_t)(nb1 > 0 ? nb1 : 1);
-  if (s1 % 8 != 0 || s2 % 8 != 0) return set_error("gemm operand batch strides must be multiples of 8 elements");
+  if (s1 % 8 != 0 || s2 % 8 != 0) return set_error("tensor-map operand batch strides must be multiples of 8 elements");
   if (s1 == 0) s1 = 8;
   if (s2 == 0) s2 = 8;
+  static thread_local std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+  const MapKey key{base, inner, rows, nb1, nb2, ld, s1, s2, box_rows};
+  auto it = cache.find(key);
+  if (it != cache.end()) {
+    *map = it->second;
+    return 0;
+  }
   cuuint64_t dims[4] = {inner, rows, nb1 ? nb1 : 1, nb2 ? nb2 : 1};
   cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)s1 * 2, (cuuint64_t)s2 * 2};
   cuuint32_t box[4] = {64, box_rows, 1, 1};
@@ -633,7 +663,13 @@ static int make_map(CUtensorMap* map, const void* base, uint64_t inner, uint64_t
              (unsigned long long)dims[3], (long long)ld, (long long)s1, (long long)s2, box_rows);
     return set_error(buf);
   }
+  if (cache.size() > 8192) cache.clear();
+  cache.emplace(key, *map);
   return 0;
+}
+static inline int make_map(CUtensorMap* map, const void* base, uint64_t inner, uint64_t rows, uint64_t nb1, uint64_t nb2,
+                           int64_t ld, int64_t s1, int64_t s2, uint32_t box_rows) {
+  return bb::make_tmap_bf16_4d(map, base, inner, rows, nb1, nb2, ld, s1, s2, box_rows);
 }
 
 // ---- optional per-launch timing (bench.py roofline): CUDA events around every gemm_tc_kernel launch

@@ -198,6 +198,11 @@ def _flash_args(q, k, v, o, lse, B, H, nq, nk, ldq, ldk, ldv, ldo, kmask, bias, 
     return a
 
 
+def set_attn_tc(mode: int) -> int:
+    """0: mma.sync attention kernels only; 1: tcgen05 kernels for nk >= 64 (default); 2: tcgen05 wherever supported."""
+    return int(_lib.load().bb_set_attn_tc(int(mode)))
+
+
 def flash_fwd(q, k, v, B, H, nq, nk, ldq, ldk, ldv, kmask=None, bias=None, drop=NO_DROP):
     """fused attention core (bb_flash_fwd): q/k/v are bf16 tensors whose data_ptr is element (0,0,0,0) of the
     (B, rows, H, 64) view with row stride ld*; -> (o (B,nq,H*64) bf16, lse (B,H,nq) f32)."""
