@@ -85,6 +85,13 @@ int bb_bev_lift_index(const float* depths, const float* T_c2w, const float* S_w2
                       int Hf, int Wf, float depth_scale, float fx, float fy, float cx, float cy, int map_dim,
                       float map_res, float y_clip, int32_t* cell_idx, float* pc_out, void* stream);
 
+/* Cell index of a ready-made ego-frame point cloud (PointCloud.project_bev, pretrain_src/model/bev_utils.py:381-406,
+ * map_nav_src/models/bev_utils.py:382-401): pc f32 (npoints, 3), no_depth u8 (npoints) or NULL -> cell_idx int32
+ * (npoints): D*round(z/res + (D-1)/2) + round(x/res + (D-1)/2) (round half to even), -1 when the point has no depth,
+ * falls outside the map or lies above y_clip. */
+int bb_bev_cell_index(const float* pc, const uint8_t* no_depth, int64_t npoints, int map_dim, float map_res, float y_clip,
+                      int32_t* cell_idx, void* stream);
+
 /* Scatter-mean pool of point features into BEV cells (torch_scatter.scatter_mean call sites
  * bev_utils.py:407-410): feats f32 (B, P, C) -> bev f32 (B, D*D, C) and/or bev_bf16; deterministic
  * (points of a cell are summed in ascending point order). ob_mask u8 (B, D*D) = !(max==0 && min==0)

@@ -182,6 +182,12 @@ def bev_lift_index(depths, T_c2w, S_w2c, T_w2c, map_dim, map_res, depth_scale=10
     return idx.to(torch.int32), (pc if want_pc else None)
 
 
+def bev_cell_index(pc, no_depth, map_dim, map_res, y_clip=0.5):
+    from oracle import bevbert_ref as R
+    nd = no_depth if no_depth is not None else torch.zeros(pc.shape[:-1], dtype=torch.bool)
+    return R.cell_index(pc, nd.bool(), map_dim, map_res, y_clip).to(torch.int32)
+
+
 def bev_scatter_mean(feats, cell_idx, ncell, want_f32=True, want_bf16=True):
     from oracle import bevbert_ref as R
     feats = feats.float()                      # bf16 wire features pool in fp32, like the kernel
@@ -378,7 +384,7 @@ def set_attn_tc(mode):
     return 1
 
 
-_NAMES = ["set_attn_tc", "MtTable", "mt_cast_bf16", "mt_sumsq", "adamw_step", "flash_fwd", "flash_bwd", "attn_scores_fwd", "attn_scores_bwd", "gemm_profile", "gemm_profile_records", "native_sublayers", "attn_desc", "ffn_desc", "pano_desc", "sublayer_ws_bytes", "sublayer_fwd", "sublayer_bwd", "gemm", "act_dtype", "drop_params", "launch_count", "reset_launch_count", "bev_lift_index",
+_NAMES = ["bev_cell_index", "set_attn_tc", "MtTable", "mt_cast_bf16", "mt_sumsq", "adamw_step", "flash_fwd", "flash_bwd", "attn_scores_fwd", "attn_scores_bwd", "gemm_profile", "gemm_profile_records", "native_sublayers", "attn_desc", "ffn_desc", "pano_desc", "sublayer_ws_bytes", "sublayer_fwd", "sublayer_bwd", "gemm", "act_dtype", "drop_params", "launch_count", "reset_launch_count", "bev_lift_index",
           "bev_scatter_mean", "bev_scatter_sem", "cast_to_act", "cast_to_f32", "dropout_act", "layernorm_fwd",
           "layernorm_bwd", "colsum", "softmax_fwd", "softmax_bwd", "embed_sum", "embed_scatter_grad", "gather_rows",
           "scatter_add_rows", "gelu_bwd", "relu_bwd", "add_rows", "scale_rows_", "segment_wsum", "segment_wsum_bwd",

@@ -594,3 +594,85 @@ def test_tcgen05_attention_forward_matches_fp32_and_mma_sync_paths(K, nq, nk, cr
     assert rel_l2(o[:2], o_ref[:2]) < 4e-3 and float(o_ref[2].float().abs().max()) == 0.0
     # identical dropout decisions: the dropped outputs agree as closely as the undropped ones
     assert rel_l2(od[:2], od_ref[:2]) < 6e-3 and (lsed[fin] - lse_ref[fin]).abs().max() < 2e-3
+
+
+def test_project_bev_reference_entry_point_bit_exact(K):
+    """PointCloud.project_bev(pc, mask, feat[, sem]) -- the entry point the agents call (map_nav_src/r2r/agent.py:170) --
+    against the oracle's cell_index + scatter_mean: indices, features, semantics and masks bit for bit, including
+    boundary points (exact .5 cell edges -> round half to even), y == clip, points outside, and a ragged list input."""
+    from bevbert_b200.model.bev_utils import PointCloud
+    from oracle import bevbert_ref as R
+    import math
+    D, res = 21, 0.5
+    pcl = PointCloud(math.radians(90), 1, 14, 14, D, res)
+    g = torch.Generator().manual_seed(5)
+    B, N, C = 3, 1500, 768
+    pc = (torch.rand(B, N, 3, generator=g) - 0.5) * 14.0
+    pc[0, :6] = torch.tensor([[0.0, 0.0, 0.0], [0.25, 0.5, 0.75], [-0.25, 0.5000001, 1.25], [5.25, 0.0, -5.25],
+                              [5.26, 0.0, 0.0], [-5.25, 0.2, 5.24]])
+    nod = torch.rand(B, N, generator=g) < 0.05
+    feat = torch.randn(B, N, C, generator=g)
+    sem = torch.nn.functional.one_hot(torch.randint(0, 40, (B, N), generator=g), 40).double()
+    bev, ob, s, sm = pcl.project_bev(pc.cuda(), nod.cuda(), feat.cuda(), sem.cuda())
+    idx = R.cell_index(pc, nod, D, res, 0.5)
+    for i in range(B):
+        rb = R.scatter_mean(feat[i], idx[i], D * D).reshape(D, D, C)
+        assert torch.equal(bev[i].cpu(), rb)
+        assert torch.equal(ob[i].cpu(), ~((rb.max(-1)[0] == 0) & (rb.min(-1)[0] == 0)))
+        rs = R.scatter_mean(sem[i], idx[i], D * D).reshape(D, D, 40)
+        rs[rs > 0] = 1
+        assert torch.equal(s[i].cpu(), rs) and torch.equal(sm[i].cpu(), rs.sum(2) > 0)
+    # agent-side variant: no semantics, ragged per-sample clouds
+    lens = [1500, 700, 1]
+    bev2, ob2 = pcl.project_bev([pc[i, :n].cuda() for i, n in enumerate(lens)], [nod[i, :n].cuda() for i, n in enumerate(lens)],
+                                [feat[i, :n].cuda() for i, n in enumerate(lens)])
+    for i, n in enumerate(lens):
+        rb = R.scatter_mean(feat[i, :n], idx[i, :n], D * D).reshape(D, D, C)
+        assert torch.equal(bev2[i].cpu(), rb)
+
+
+@pytest.mark.parametrize("nq,nk,cross,mode", [(441, 441, False, 1), (441, 80, True, 1), (80, 441, True, 1), (80, 80, False, 1),
+                                              (130, 200, True, 1), (100, 512, True, 1), (512, 441, True, 1),
+                                              (36, 36, False, 2), (23, 80, True, 2), (5, 7, True, 2)])
+def test_tcgen05_attention_backward_matches_fp32_autograd(K, nq, nk, cross, mode):
+    """csrc/attn_tc.cu backward (two tcgen05 passes: dQ per query tile, dK/dV per key tile) vs fp32 torch autograd with
+    key masks (-10000 / -inf) and ragged tails, outputs written into packed views; plus dropout replay against the
+    mma.sync backward on the same forward state."""
+    B, H, Hd = 2, 12, 768
+    if not cross:
+        qkv = rnd(B * nq, 3 * Hd, scale=0.8).cuda()
+        q, k, v, ldq, ldk, ldv = qkv, qkv[:, Hd:], qkv[:, 2 * Hd:], 3 * Hd, 3 * Hd, 3 * Hd
+    else:
+        q = rnd(B * nq, Hd, scale=0.8).cuda()
+        kv = rnd(B * nk, 2 * Hd, scale=0.8, seed=1).cuda()
+        k, v, ldq, ldk, ldv = kv, kv[:, Hd:], Hd, 2 * Hd, 2 * Hd
+    kmask = torch.zeros(B, nk)
+    kmask[1, nk // 2:] = -10000.0
+    kmask[0, -3:] = float("-inf")
+    kmask = kmask.cuda()
+    dout = rnd(B, nq, Hd, scale=0.5, seed=2).cuda()
+    th, sc = K.drop_params(0.1)
+    prev = K.set_attn_tc(mode)
+    try:
+        o, lse = K.flash_fwd(q, k, v, B, H, nq, nk, ldq, ldk, ldv, kmask, None)
+        dpack = torch.zeros(B * nk, 2 * Hd, dtype=BF, device="cuda")
+        dqo = torch.zeros(B * nq, Hd, dtype=BF, device="cuda")
+        K.flash_bwd(q, k, v, o, lse, dout, B, H, nq, nk, ldq, ldk, ldv, kmask, None,
+                    out=(dqo, Hd, dpack, 2 * Hd, dpack[:, Hd:], 2 * Hd))
+        od, lsed = K.flash_fwd(q, k, v, B, H, nq, nk, ldq, ldk, ldv, kmask, None, (77, th, sc))
+        dq_d, dk_d, dv_d = K.flash_bwd(q, k, v, od, lsed, dout, B, H, nq, nk, ldq, ldk, ldv, kmask, None, (77, th, sc))
+        K.set_attn_tc(0)
+        dq_r, dk_r, dv_r = K.flash_bwd(q, k, v, od, lsed, dout, B, H, nq, nk, ldq, ldk, ldv, kmask, None, (77, th, sc))
+    finally:
+        K.set_attn_tc(prev)
+    ro, _, (qh, kh, vh, _) = _flash_ref(q, k, v, B, H, nq, nk, ldq, ldk, ldv, kmask, None)
+    ro.backward(dout.float())
+
+    def unheads(t, n):
+        return t.permute(0, 2, 1, 3).reshape(B, n, Hd)
+    assert rel_l2(dqo.view(B, nq, Hd), unheads(qh.grad, nq)) < 1.2e-2
+    assert rel_l2(dpack[:, :Hd].reshape(B, nk, Hd), unheads(kh.grad, nk)) < 1.2e-2
+    assert rel_l2(dpack[:, Hd:].reshape(B, nk, Hd), unheads(vh.grad, nk)) < 1.2e-2
+    assert torch.isfinite(dqo.float()).all() and torch.isfinite(dpack.float()).all()
+    # same dropout mask in both backward implementations
+    assert rel_l2(dq_d, dq_r) < 1.2e-2 and rel_l2(dk_d, dk_r) < 1.2e-2 and rel_l2(dv_d, dv_r) < 1.2e-2

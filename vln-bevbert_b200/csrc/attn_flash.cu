@@ -616,6 +616,7 @@ extern "C" int bb_flash_bwd(const bb_flash_args* a, void* stream) {
   using namespace bb;
   fa::Params p;
   if (int e = fa::fill(p, a, true)) return e;
+  if (fat::bwd_supported(a)) return fat::launch_bwd(a, stream);   // tcgen05 / TMA core (attn_tc.cu)
   const dim3 gq((unsigned)((a->nq + fa::BM - 1) / fa::BM), (unsigned)a->H, (unsigned)a->B);
   const dim3 gk((unsigned)((a->nk + fa::BM - 1) / fa::BM), (unsigned)a->H, (unsigned)a->B);
   launch_pdl(fa::flash_bwd_dq_kernel, gq, dim3(fa::NT), 0, (cudaStream_t)stream, p);

@@ -89,6 +89,24 @@ __device__ __forceinline__ uint32_t mix_pair(uint32_t rowhash, uint32_t pair) {
   x ^= x >> 15;
   return x;
 }
+// explicit shared-space accesses: the carve-up of the dynamic shared memory goes through integer arithmetic, after which
+// the compiler no longer knows the address space and emits generic LD / ST (measured: the top long-scoreboard stalls)
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float lds_f(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_f(uint32_t addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void sts_u4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
 __device__ __forceinline__ void named_sync_256() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 __global__ void __launch_bounds__(NT, 1)
@@ -207,8 +225,9 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
     const int64_t grow = ((int64_t)b * p.H + h) * p.nq + q0 + row;
     const uint32_t rh = p.thresh ? rng_u32(p.seed, (uint64_t)grow) : 0u;
     const uint32_t t16 = p.thresh >> 16;
-    uint8_t* prow = sP + hf * P_BYTES + (row >> 3) * 1024 + (row & 7) * 128;
+    const uint32_t prow = smem_u32(sP) + hf * P_BYTES + (row >> 3) * 1024 + (row & 7) * 128;
     const int sw = row & 7;
+    const uint32_t a_skm = smem_u32(skm), a_smax = smem_u32(smax), a_ssum = smem_u32(ssum);
     uint32_t pe_phase = 0;
     float m_run = -INFINITY, l_run = 0.f;
     float o_run[32];
@@ -222,7 +241,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
       // log2-domain additive key mask of this super-block (previous one fully consumed: o_read / s_full ordering)
       for (int i = st; i < p.sbk; i += 256) {
         const int col = key0 + i;
-        skm[i] = i < nkeys ? (p.kmask ? __ldg(p.kmask + (int64_t)b * p.nk + col) * LOG2E : 0.f) : -INFINITY;
+        sts_f(a_skm + i * 4, i < nkeys ? (p.kmask ? __ldg(p.kmask + (int64_t)b * p.nk + col) * LOG2E : 0.f) : -INFINITY);
       }
       named_sync_256();
       FAT_STAMP(1);
@@ -238,10 +257,10 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
             uint32_t r[32];
             tmem_ld32(trow + S_COL + j * KB + c, r);
             tmem_ld_wait32(r);
-            const float4* km4 = reinterpret_cast<const float4*>(skm + j * KB + c);
+            const uint32_t km4 = a_skm + (j * KB + c) * 4;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              const float4 km = km4[i];
+              const float4 km = lds_f4(km4 + i * 16);
               mx = fmaxf(mx, fmaf(__uint_as_float(r[4 * i + 0]), p.a2, km.x));
               mx = fmaxf(mx, fmaf(__uint_as_float(r[4 * i + 1]), p.a2, km.y));
               mx = fmaxf(mx, fmaf(__uint_as_float(r[4 * i + 2]), p.a2, km.z));
@@ -250,10 +269,10 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
           }
         }
       }
-      smax[hf * BM + row] = mx;
+      sts_f(a_smax + (hf * BM + row) * 4, mx);
       named_sync_256();
       FAT_STAMP(3);
-      const float m = fmaxf(smax[row], smax[BM + row]);
+      const float m = fmaxf(lds_f(a_smax + row * 4), lds_f(a_smax + (BM + row) * 4));
       const float ms = m == -INFINITY ? 0.f : m;
       // ---- pass 2: probabilities -> bf16 P blocks in shared memory (A operand of the PV product)
       float lsum = 0.f;
@@ -266,11 +285,11 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
             uint32_t r[32];
             tmem_ld32(trow + S_COL + j * KB + c, r);
             tmem_ld_wait32(r);
-            const float4* km4 = reinterpret_cast<const float4*>(skm + j * KB + c);
+            const uint32_t km4 = a_skm + (j * KB + c) * 4;
             const uint32_t pair0 = (uint32_t)(key0 + j * KB + c) >> 1;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              const float4 km = km4[i];
+              const float4 km = lds_f4(km4 + i * 16);
               float e0 = ex2f(fmaf(__uint_as_float(r[4 * i + 0]), p.a2, km.x) - ms);
               float e1 = ex2f(fmaf(__uint_as_float(r[4 * i + 1]), p.a2, km.y) - ms);
               float e2 = ex2f(fmaf(__uint_as_float(r[4 * i + 2]), p.a2, km.z) - ms);
@@ -293,17 +312,17 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
 #pragma unroll
           for (int i = 0; i < 4; ++i) {   // 16-byte chunk (c/8 + i) of this row, XOR-swizzled by the row (128B swizzle)
             const int ch = (c >> 3) + i;
-            *reinterpret_cast<uint4*>(prow + ((ch ^ sw) << 4)) = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+            sts_u4(prow + ((ch ^ sw) << 4), pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
           }
         }
         fence_proxy_async();          // generic-proxy stores -> visible to the tensor core's async-proxy reads
         mbar_arrive(&p_full[hf]);
         pe_phase ^= 1;
       }
-      ssum[hf * BM + row] = lsum;
+      sts_f(a_ssum + (hf * BM + row) * 4, lsum);
       named_sync_256();
       FAT_STAMP(4);
-      const float l = ssum[row] + ssum[BM + row];
+      const float l = lds_f(a_ssum + row * 4) + lds_f(a_ssum + (BM + row) * 4);
       // ---- O of this super-block: columns [32 hf, 32 hf + 32) of the row
       mbar_wait(o_full, sb & 1);
       tc_fence_after();
@@ -346,14 +365,338 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
   }
 }
 
+
+// ================================================================================================ backward
+// Two passes over the (query tile x key tile) grid of a (sample, head), both with 128 x 128 score tiles in TMEM and the
+// thread <-> query-row mapping of the forward kernel:
+//   MODE 0 (CTA = 128 queries): D = rowsum(dO o O);  for each key tile: S = Q K^T, dP = dO V^T  ->  dS  ->  dQ += dS K
+//   MODE 1 (CTA = 128 keys)   : for each query tile: S = Q K^T, dP = dO V^T -> Pdrop, dS -> dV += Pdrop^T dO, dK += dS^T Q
+// with P = 2^(a2 S + kmask - lse), dS = alpha P o (drop(dP) - D).  S and dP are two tcgen05.mma groups into TMEM columns
+// [0,128) and [128,256); the softmax warps turn them into bf16 Pdrop / dS tiles in shared memory ([query][key], 128B
+// swizzle), which the second round of MMAs reads as a K-major A operand (dS K) or as an MN-major A operand (P^T dO,
+// dS^T Q); accumulators (dQ, or dV and dK) live in TMEM columns [256,384) for the whole CTA.  No atomics.
+constexpr int B_S_COL = 0, B_DP_COL = 128, B_ACC0 = 256, B_ACC1 = 320;
+constexpr int TILE_BYTES = 128 * 128;    // 128 rows x 64 bf16
+
+struct BwdParams {
+  const bf16 *o, *dout;
+  bf16 *dq, *dk, *dv;
+  int64_t o_bs, do_bs, dq_bs, dk_bs, dv_bs;
+  int ldo, lddo, lddq, lddk, lddv;
+  const float* lse;
+  float* dsum;
+  const float* kmask;
+  int B, H, nq, nk;
+  float a2, alpha;
+  uint64_t seed;
+  uint32_t thresh;
+  float scale;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(NT, 1)
+attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk,
+                   const __grid_constant__ CUtensorMap tv, const __grid_constant__ CUtensorMap tdo, const BwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sR0 = smem;                          // resident: Q_i (MODE 0) / K_t (MODE 1)
+  uint8_t* sR1 = sR0 + TILE_BYTES;              // resident: dO_i       / V_t
+  uint8_t* sST = sR1 + TILE_BYTES;              // 2 stages x (K_j | V_j) or (Q_i | dO_i)
+  uint8_t* sPD = sST + 4 * TILE_BYTES;          // Pdrop tile: 2 key blocks x [128 q][64 k]   (MODE 1)
+  uint8_t* sDS = sPD + 2 * TILE_BYTES;          // dS tile, same layout
+  float* skm = reinterpret_cast<float*>(sDS + 2 * TILE_BYTES);   // [2][128] log2-domain key mask per stage / tile
+  float* srow = skm + 256;                                         // [128] dsum exchange (MODE 0)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(srow + 128);
+  uint64_t* r_full = bars + 0;
+  uint64_t* st_full = bars + 1;     // [2]
+  uint64_t* st_empty = bars + 3;    // [2]
+  uint64_t* sdp_full = bars + 5;
+  uint64_t* sdp_empty = bars + 6;
+  uint64_t* ds_full = bars + 7;
+  uint64_t* ds_empty = bars + 8;
+  uint64_t* acc_full = bars + 9;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 10);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t0 = blockIdx.x * BM, h = blockIdx.y, b = blockIdx.z;   // first query (MODE 0) / key (MODE 1) of this CTA
+  const int ntiles = MODE == 0 ? (p.nk + BM - 1) / BM : (p.nq + BM - 1) / BM;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tq);
+      tma_prefetch_desc(&tk);
+      tma_prefetch_desc(&tv);
+      tma_prefetch_desc(&tdo);
+      mbar_init(r_full, 1);
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&st_full[i], 1);
+        mbar_init(&st_empty[i], 1);
+      }
+      mbar_init(sdp_full, 1);
+      mbar_init(sdp_empty, 256);
+      mbar_init(ds_full, 256);
+      mbar_init(ds_empty, 1);
+      mbar_init(acc_full, 1);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_ptr_smem, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();
+  pdl_trigger();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // resident operands
+      mbar_expect_tx(r_full, 2 * TILE_BYTES);
+      if (MODE == 0) {
+        tma_load_4d(sR0, &tq, r_full, 0, t0, h, b);
+        tma_load_4d(sR1, &tdo, r_full, 0, t0, h, b);
+      } else {
+        tma_load_4d(sR0, &tk, r_full, 0, t0, h, b);
+        tma_load_4d(sR1, &tv, r_full, 0, t0, h, b);
+      }
+      auto load_stage = [&](int tile) {
+        const int s = tile & 1;
+        uint8_t* d0 = sST + s * 2 * TILE_BYTES;
+        mbar_expect_tx(&st_full[s], 2 * TILE_BYTES);
+        if (MODE == 0) {
+          tma_load_4d(d0, &tk, &st_full[s], 0, tile * BM, h, b);
+          tma_load_4d(d0 + TILE_BYTES, &tv, &st_full[s], 0, tile * BM, h, b);
+        } else {
+          tma_load_4d(d0, &tq, &st_full[s], 0, tile * BM, h, b);
+          tma_load_4d(d0 + TILE_BYTES, &tdo, &st_full[s], 0, tile * BM, h, b);
+        }
+      };
+      load_stage(0);
+      const uint32_t idesc_s = umma_idesc_bf16(BM, 128, 0, 0);
+      const uint32_t idesc_acc = MODE == 0 ? umma_idesc_bf16(BM, 64, 0, 1) : umma_idesc_bf16(BM, 64, 1, 1);
+      const uint32_t aR0 = smem_u32(sR0), aR1 = smem_u32(sR1), aPD = smem_u32(sPD), aDS = smem_u32(sDS);
+      mbar_wait(r_full, 0);
+      for (int tile = 0; tile < ntiles; ++tile) {
+        const int s = tile & 1;
+        if (tile + 1 < ntiles) {            // prefetch the next stage (its previous user, tile-1, must have retired)
+          if (tile >= 1) mbar_wait(&st_empty[s ^ 1], ((tile - 1) >> 1) & 1);
+          load_stage(tile + 1);
+        }
+        mbar_wait(&st_full[s], (tile >> 1) & 1);
+        if (tile > 0) mbar_wait(sdp_empty, (tile - 1) & 1);
+        tc_fence_after();
+        const uint32_t a0 = smem_u32(sST + s * 2 * TILE_BYTES), a1 = a0 + TILE_BYTES;
+        // S = Q K^T and dP = dO V^T (both operands K-major, N = 128)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t dq_ = umma_smem_desc((MODE == 0 ? aR0 : a0) + k * 32, 16, 1024);
+          const uint64_t dk_ = umma_smem_desc((MODE == 0 ? a0 : aR0) + k * 32, 16, 1024);
+          umma_bf16_ss(tmem_base + B_S_COL, dq_, dk_, idesc_s, k > 0 ? 1u : 0u);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t ddo = umma_smem_desc((MODE == 0 ? aR1 : a1) + k * 32, 16, 1024);
+          const uint64_t dv_ = umma_smem_desc((MODE == 0 ? a1 : aR1) + k * 32, 16, 1024);
+          umma_bf16_ss(tmem_base + B_DP_COL, ddo, dv_, idesc_s, k > 0 ? 1u : 0u);
+        }
+        umma_commit(sdp_full);
+        mbar_wait(ds_full, tile & 1);
+        tc_fence_after();
+        if (MODE == 0) {
+          // dQ += dS K_j : A = dS K-major (two 64-key blocks), B = K_j [key][d] as MN-major (N = d, K = key)
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)
+            umma_bf16_ss(tmem_base + B_ACC0, umma_smem_desc(aDS + (kk >> 2) * TILE_BYTES + (kk & 3) * 32, 16, 1024),
+                         umma_smem_desc(a0 + kk * 2048, 8192, 1024), idesc_acc, (tile > 0 || kk > 0) ? 1u : 0u);
+        } else {
+          // dV += Pdrop^T dO_i, dK += dS^T Q_i : A = [q][key] tile read MN-major (M = key, K = q), B = [q][d] MN-major
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)
+            umma_bf16_ss(tmem_base + B_ACC0, umma_smem_desc(aPD + kk * 2048, TILE_BYTES, 1024),
+                         umma_smem_desc(a1 + kk * 2048, 8192, 1024), idesc_acc, (tile > 0 || kk > 0) ? 1u : 0u);
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)
+            umma_bf16_ss(tmem_base + B_ACC1, umma_smem_desc(aDS + kk * 2048, TILE_BYTES, 1024),
+                         umma_smem_desc(a0 + kk * 2048, 8192, 1024), idesc_acc, (tile > 0 || kk > 0) ? 1u : 0u);
+        }
+        umma_commit(ds_empty);
+        umma_commit(&st_empty[s]);
+      }
+      umma_commit(acc_full);
+    }
+    __syncwarp();
+  } else {
+    const int quarter = warp & 3;
+    const int hf = (warp - 1) >> 2;           // key columns [64 hf, 64 hf + 64) of every tile
+    const int row = quarter * 32 + lane;      // query row of the tile = TMEM lane
+    const int st = threadIdx.x - 32;
+    const uint32_t trow = tmem_base + (uint32_t(quarter * 32) << 16);
+    const uint32_t t16 = p.thresh >> 16;
+    const int sw = row & 7;
+    const uint32_t rowoff = hf * TILE_BYTES + (row >> 3) * 1024 + (row & 7) * 128;
+    const uint32_t a_skm = smem_u32(skm), a_srow = smem_u32(srow), a_sDS = smem_u32(sDS), a_sPD = smem_u32(sPD);
+    // per-row state of the CURRENT query tile
+    float lse_r = INFINITY, dsum_r = 0.f;
+    uint32_t rh = 0;
+    auto load_row_state = [&](int q) {        // q = global query index of this thread's row
+      const int64_t gr = ((int64_t)b * p.H + h) * p.nq + q;
+      if (q < p.nq) {
+        lse_r = __ldg(p.lse + gr);
+        if (MODE == 1) dsum_r = __ldg(p.dsum + gr);
+      } else {
+        lse_r = INFINITY;
+        dsum_r = 0.f;
+      }
+      rh = p.thresh ? rng_u32(p.seed, (uint64_t)gr) : 0u;
+    };
+    if (MODE == 0) {
+      load_row_state(t0 + row);
+      // D = rowsum(dO o O) for this row, shared with the other key half through smem and saved for MODE 1
+      if (hf == 0) {
+        float acc = 0.f;
+        if (t0 + row < p.nq) {
+          const uint4* po = reinterpret_cast<const uint4*>(p.o + (int64_t)b * p.o_bs + (int64_t)(t0 + row) * p.ldo + h * 64);
+          const uint4* pd = reinterpret_cast<const uint4*>(p.dout + (int64_t)b * p.do_bs + (int64_t)(t0 + row) * p.lddo + h * 64);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const uint4 a = __ldg(po + i), d = __ldg(pd + i);
+            const __nv_bfloat162* ap = reinterpret_cast<const __nv_bfloat162*>(&a);
+            const __nv_bfloat162* dp = reinterpret_cast<const __nv_bfloat162*>(&d);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 x = __bfloat1622float2(ap[e]), y = __bfloat1622float2(dp[e]);
+              acc = fmaf(x.x, y.x, acc);
+              acc = fmaf(x.y, y.y, acc);
+            }
+          }
+          p.dsum[((int64_t)b * p.H + h) * p.nq + t0 + row] = acc;
+        }
+        sts_f(a_srow + row * 4, acc);
+      }
+      named_sync_256();
+      dsum_r = lds_f(a_srow + row * 4);
+    }
+
+    for (int tile = 0; tile < ntiles; ++tile) {
+      const int key0 = MODE == 0 ? tile * BM : t0;
+      uint32_t km = a_skm + (tile & 1) * 512;
+      if (MODE == 1) load_row_state(tile * BM + row);
+      if (MODE == 0 || tile == 0) {
+        if (st < 128) {
+          const int col = key0 + st;
+          sts_f(km + st * 4, col < p.nk ? (p.kmask ? __ldg(p.kmask + (int64_t)b * p.nk + col) * LOG2E : 0.f) : -INFINITY);
+        }
+        named_sync_256();
+      } else {
+        km = a_skm;
+      }
+      mbar_wait(sdp_full, tile & 1);
+      tc_fence_after();
+      if (tile > 0) mbar_wait(ds_empty, (tile - 1) & 1);      // the previous tile's Pdrop / dS have been consumed
+#pragma unroll
+      for (int c = 0; c < 64; c += 32) {
+        const int col0 = hf * 64 + c;
+        uint32_t rs[32], rp[32];
+        tmem_ld32(trow + B_S_COL + col0, rs);
+        tmem_ld32(trow + B_DP_COL + col0, rp);
+        tmem_ld_wait32(rs);
+        tmem_ld_wait32(rp);
+        uint32_t pk_p[16], pk_s[16];
+        const uint32_t km4 = km + col0 * 4;
+        const uint32_t pair0 = (uint32_t)(key0 + col0) >> 1;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 kmv = lds_f4(km4 + i * 16);
+          float pe[4], ge[4];
+          pe[0] = ex2f(fmaf(__uint_as_float(rs[4 * i + 0]), p.a2, kmv.x) - lse_r);
+          pe[1] = ex2f(fmaf(__uint_as_float(rs[4 * i + 1]), p.a2, kmv.y) - lse_r);
+          pe[2] = ex2f(fmaf(__uint_as_float(rs[4 * i + 2]), p.a2, kmv.z) - lse_r);
+          pe[3] = ex2f(fmaf(__uint_as_float(rs[4 * i + 3]), p.a2, kmv.w) - lse_r);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) ge[e] = __uint_as_float(rp[4 * i + e]);
+          float pd[4] = {pe[0], pe[1], pe[2], pe[3]};
+          if (p.thresh) {
+            const uint32_t x0 = mix_pair(rh, pair0 + 2 * i), x1 = mix_pair(rh, pair0 + 2 * i + 1);
+            const bool k0 = (x0 & 0xFFFFu) >= t16, k1 = (x0 >> 16) >= t16, k2 = (x1 & 0xFFFFu) >= t16, k3 = (x1 >> 16) >= t16;
+            ge[0] = k0 ? ge[0] * p.scale : 0.f;
+            ge[1] = k1 ? ge[1] * p.scale : 0.f;
+            ge[2] = k2 ? ge[2] * p.scale : 0.f;
+            ge[3] = k3 ? ge[3] * p.scale : 0.f;
+            if (MODE == 1) {
+              pd[0] = k0 ? pe[0] * p.scale : 0.f;
+              pd[1] = k1 ? pe[1] * p.scale : 0.f;
+              pd[2] = k2 ? pe[2] * p.scale : 0.f;
+              pd[3] = k3 ? pe[3] * p.scale : 0.f;
+            }
+          }
+          pk_s[2 * i] = pack2(pe[0] * (ge[0] - dsum_r) * p.alpha, pe[1] * (ge[1] - dsum_r) * p.alpha);
+          pk_s[2 * i + 1] = pack2(pe[2] * (ge[2] - dsum_r) * p.alpha, pe[3] * (ge[3] - dsum_r) * p.alpha);
+          if (MODE == 1) {
+            pk_p[2 * i] = pack2(pd[0], pd[1]);
+            pk_p[2 * i + 1] = pack2(pd[2], pd[3]);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint32_t off = rowoff + ((((c >> 3) + i) ^ sw) << 4);
+          sts_u4(a_sDS + off, pk_s[4 * i], pk_s[4 * i + 1], pk_s[4 * i + 2], pk_s[4 * i + 3]);
+          if (MODE == 1) sts_u4(a_sPD + off, pk_p[4 * i], pk_p[4 * i + 1], pk_p[4 * i + 2], pk_p[4 * i + 3]);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(sdp_empty);       // S / dP columns may be overwritten by the next tile
+      fence_proxy_async();
+      mbar_arrive(ds_full);
+    }
+
+    // ---- accumulators -> bf16 rows (MODE 0: dQ rows = queries; MODE 1: dV / dK rows = keys)
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    const int nrows = MODE == 0 ? p.nq : p.nk;
+    const bool valid = t0 + row < nrows;
+    auto store32 = [&](uint32_t col, bf16* dst) {      // the TMEM load is warp-collective: only the store is predicated
+      uint32_t r[32];
+      tmem_ld32(trow + col, r);
+      tmem_ld_wait32(r);
+      if (valid) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          reinterpret_cast<uint4*>(dst)[i] =
+              make_uint4(pack2(__uint_as_float(r[8 * i]), __uint_as_float(r[8 * i + 1])),
+                         pack2(__uint_as_float(r[8 * i + 2]), __uint_as_float(r[8 * i + 3])),
+                         pack2(__uint_as_float(r[8 * i + 4]), __uint_as_float(r[8 * i + 5])),
+                         pack2(__uint_as_float(r[8 * i + 6]), __uint_as_float(r[8 * i + 7])));
+      }
+    };
+    const int64_t grow_ = t0 + row;
+    if (MODE == 0) {
+      store32(B_ACC0 + hf * 32, p.dq + (int64_t)b * p.dq_bs + grow_ * p.lddq + h * 64 + hf * 32);
+    } else {
+      store32(B_ACC0 + hf * 32, p.dv + (int64_t)b * p.dv_bs + grow_ * p.lddv + h * 64 + hf * 32);
+      store32(B_ACC1 + hf * 32, p.dk + (int64_t)b * p.dk_bs + grow_ * p.lddk + h * 64 + hf * 32);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 static int g_smem_optin = 0;
 static int init_once() {
   if (g_smem_optin) return 0;
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return set_error("cudaGetDevice failed");
   cudaDeviceGetAttribute(&g_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-  if (cudaFuncSetAttribute(attn_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin) != cudaSuccess)
-    return set_error("cudaFuncSetAttribute failed for attn_tc_fwd_kernel");
+  if (cudaFuncSetAttribute(attn_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin) != cudaSuccess ||
+      cudaFuncSetAttribute(attn_tc_bwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin) != cudaSuccess ||
+      cudaFuncSetAttribute(attn_tc_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin) != cudaSuccess)
+    return set_error("cudaFuncSetAttribute failed for the attn_tc kernels");
   return 0;
 }
 
@@ -410,6 +753,43 @@ int launch_fwd(const bb_flash_args* a, void* stream) {
   launch_pdl(attn_tc_fwd_kernel, grid, dim3(NT), smem, (cudaStream_t)stream, tq, tk, tv, p);
   count_launch();
   return check_launch("attn_tc_fwd_kernel");
+}
+
+bool bwd_supported(const bb_flash_args* a) {
+  if (!fwd_supported(a) || a->dbias != nullptr) return false;
+  const uintptr_t al = reinterpret_cast<uintptr_t>(a->dout) | reinterpret_cast<uintptr_t>(a->dq) |
+                       reinterpret_cast<uintptr_t>(a->dk) | reinterpret_cast<uintptr_t>(a->dv);
+  if (al & 15) return false;
+  if ((a->lddo | a->lddq | a->lddk | a->lddv) % 8) return false;
+  if ((a->do_bs | a->dq_bs | a->dk_bs | a->dv_bs) % 8) return false;
+  return true;
+}
+
+int launch_bwd(const bb_flash_args* a, void* stream) {
+  if (int e = init_once()) return e;
+  BwdParams p;
+  memset(&p, 0, sizeof(p));
+  p.o = (const bf16*)a->o; p.dout = (const bf16*)a->dout;
+  p.dq = (bf16*)a->dq; p.dk = (bf16*)a->dk; p.dv = (bf16*)a->dv;
+  p.o_bs = a->o_bs; p.do_bs = a->do_bs; p.dq_bs = a->dq_bs; p.dk_bs = a->dk_bs; p.dv_bs = a->dv_bs;
+  p.ldo = a->ldo; p.lddo = a->lddo; p.lddq = a->lddq; p.lddk = a->lddk; p.lddv = a->lddv;
+  p.lse = a->lse; p.dsum = a->dsum; p.kmask = a->kmask;
+  p.B = a->B; p.H = a->H; p.nq = a->nq; p.nk = a->nk;
+  p.a2 = a->alpha * LOG2E; p.alpha = a->alpha;
+  p.seed = a->seed; p.thresh = a->thresh; p.scale = a->scale;
+  CUtensorMap tq, tk, tv, tdo;
+  if (int e = make_tmap_bf16_4d(&tq, a->q, 64, a->nq, a->H, a->B, a->ldq, 64, a->q_bs, BM)) return e;
+  if (int e = make_tmap_bf16_4d(&tk, a->k, 64, a->nk, a->H, a->B, a->ldk, 64, a->k_bs, BM)) return e;
+  if (int e = make_tmap_bf16_4d(&tv, a->v, 64, a->nk, a->H, a->B, a->ldv, 64, a->v_bs, BM)) return e;
+  if (int e = make_tmap_bf16_4d(&tdo, a->dout, 64, a->nq, a->H, a->B, a->lddo, 64, a->do_bs, BM)) return e;
+  const size_t smem = 1024 + 10 * (size_t)TILE_BYTES + 384 * 4 + 128;
+  if ((int)smem > g_smem_optin) return set_error("attn_tc_bwd: shared memory budget exceeded");
+  const dim3 gq((unsigned)((a->nq + BM - 1) / BM), (unsigned)a->H, (unsigned)a->B);
+  const dim3 gk((unsigned)((a->nk + BM - 1) / BM), (unsigned)a->H, (unsigned)a->B);
+  launch_pdl(attn_tc_bwd_kernel<0>, gq, dim3(NT), smem, (cudaStream_t)stream, tq, tk, tv, tdo, p);
+  launch_pdl(attn_tc_bwd_kernel<1>, gk, dim3(NT), smem, (cudaStream_t)stream, tq, tk, tv, tdo, p);
+  count_launch(2);
+  return check_launch("attn_tc_bwd kernels");
 }
 
 }  // namespace fat

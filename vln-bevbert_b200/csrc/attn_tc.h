@@ -8,5 +8,7 @@ int tc_mode();
 int set_tc_mode(int mode);
 bool fwd_supported(const bb_flash_args* a);
 int launch_fwd(const bb_flash_args* a, void* stream);
+bool bwd_supported(const bb_flash_args* a);
+int launch_bwd(const bb_flash_args* a, void* stream);
 }  // namespace fat
 }  // namespace bb

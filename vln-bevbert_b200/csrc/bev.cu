@@ -80,6 +80,23 @@ __global__ void lift_index_kernel(const float* __restrict__ depths, const float*
   cell_idx[gid] = bad ? -1 : (int32_t)(Df * gz + gx);
 }
 
+// Cell index of an ego-frame point cloud (PointCloud.project_bev called with a ready-made cloud: the agents gather
+// the clouds of neighbouring panoramas first, map_nav_src/r2r/agent.py:115-192): same discretisation as above.
+__global__ void cell_index_kernel(const float* __restrict__ pc, const uint8_t* __restrict__ no_depth, long long n, int D,
+                                  float res, float half, float y_clip, int32_t* __restrict__ cell_idx) {
+  bb::pdl_wait();
+  bb::pdl_trigger();
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= n) return;
+  const float e0 = pc[gid * 3 + 0], e1 = pc[gid * 3 + 1], e2 = pc[gid * 3 + 2];
+  const float gx = rintf(__fadd_rn(__fdiv_rn(e0, res), half));
+  const float gz = rintf(__fadd_rn(__fdiv_rn(e2, res), half));
+  const float Df = (float)D;
+  const bool outside = (gx >= Df) || (gz >= Df) || (gx < 0.0f) || (gz < 0.0f);
+  const bool bad = (no_depth && no_depth[gid]) || outside || (e1 > y_clip) || !(gx == gx) || !(gz == gz);
+  cell_idx[gid] = bad ? -1 : (int32_t)(Df * gz + gx);
+}
+
 // ---------------------------------------------------------------------------------------------
 // Scatter-mean: block = 8 warps = 8 cells of one sample; the sample's cell indices are staged once in
 // shared memory; each warp scans them 32 at a time (ballot) and accumulates matching rows in
@@ -238,6 +255,18 @@ extern "C" int bb_bev_lift_index(const float* depths, const float* T_c2w, const 
       pc_out);
   count_launch();
   return check_launch("lift_index_kernel");
+}
+
+extern "C" int bb_bev_cell_index(const float* pc, const uint8_t* no_depth, int64_t npoints, int map_dim, float map_res,
+                                 float y_clip, int32_t* cell_idx, void* stream) {
+  using namespace bb;
+  if (!pc || !cell_idx) return set_error("bb_bev_cell_index: null argument");
+  if (npoints <= 0) return 0;
+  const float half = (float)((map_dim - 1) / 2.0);
+  bb::launch_pdl(cell_index_kernel, (unsigned)((npoints + 255) / 256), 256, 0, (cudaStream_t)stream, pc, no_depth,
+                 (long long)npoints, map_dim, map_res, half, y_clip, cell_idx);
+  count_launch();
+  return check_launch("cell_index_kernel");
 }
 
 template <typename FT>

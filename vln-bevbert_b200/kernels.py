@@ -255,6 +255,18 @@ def bev_lift_index(depths, T_c2w, S_w2c, T_w2c, map_dim, map_res, depth_scale=10
     return idx, pc
 
 
+def bev_cell_index(pc, no_depth, map_dim, map_res, y_clip=0.5):
+    """ego-frame cloud f32 (B,P,3) + no-depth mask bool (B,P) | None -> int32 cell index (B,P), -1 = dropped."""
+    lib = _lib.load()
+    _req(pc, torch.float32, "pc")
+    pc = pc.contiguous()
+    nd = no_depth.contiguous().to(torch.uint8) if no_depth is not None else None
+    idx = torch.empty(pc.shape[:-1], dtype=torch.int32, device=pc.device)
+    _lib.check(lib.bb_bev_cell_index(pc.data_ptr(), _p(nd), idx.numel(), map_dim, map_res, y_clip, idx.data_ptr(),
+                                     _stream()), "bb_bev_cell_index")
+    return idx
+
+
 def bev_scatter_mean(feats, cell_idx, ncell, want_f32=True, want_bf16=True):
     """feats f32 or bf16 (B,P,C) -> (bev_f32 | None, bev_bf16 | None, ob_mask bool (B,ncell), counts int32)."""
     lib = _lib.load()

@@ -59,6 +59,36 @@ class PointCloud:
         return pc.reshape(N, self.fmh, self.fmw, 3), depth[:, 0] == 0
 
     @torch.no_grad()
+    def project_bev(self, pc, no_depth_mask, pc_feat, pc_sem=None):
+        """Reference entry point, both variants: pre-training `project_bev(pc, mask, feat, sem)` ->
+        (bevs (B,D,D,C), ob_masks (B,D,D), sems (B,D,D,S), sem_masks (B,D,D)) (pretrain_src/model/bev_utils.py:381-430)
+        and agent-side `project_bev(pc, mask, feat)` -> (bevs, ob_masks) (map_nav_src/models/bev_utils.py:382-417,
+        called at map_nav_src/r2r/agent.py:170).  pc (B,N,3) ego-frame points, no_depth_mask (B,N) bool, pc_feat
+        (B,N,C) fp32, pc_sem (B,N,S) fp64 one-hots.  Ragged inputs (a python list of per-sample tensors, as the agents
+        build them from neighbouring panoramas) are padded with no-depth points."""
+        if isinstance(pc, (list, tuple)):
+            n = max(x.shape[0] for x in pc)
+            dev = pc[0].device
+
+            def pad(xs, fill=0):
+                out = xs[0].new_full((len(xs), n) + tuple(xs[0].shape[1:]), fill)
+                for i, x in enumerate(xs):
+                    out[i, :x.shape[0]] = x
+                return out
+            no_depth_mask = pad([m.bool() for m in no_depth_mask], True)
+            pc, pc_feat = pad(list(pc)), pad(list(pc_feat))
+            pc_sem = pad(list(pc_sem)) if pc_sem is not None else None
+            del dev
+        D = self.map_dim
+        B = pc.shape[0]
+        idx = K.bev_cell_index(pc.float(), no_depth_mask, D, self.map_res, self.z_clip_threshold)
+        bev, _, ob, sem, sem_mask = self.splat(idx, pc_feat.float() if pc_feat.dtype != torch.bfloat16 else pc_feat, pc_sem)
+        bevs, ob_masks = bev.view(B, D, D, -1), ob.view(B, D, D)
+        if pc_sem is None:
+            return bevs, ob_masks
+        return bevs, ob_masks, sem.view(B, D, D, -1), sem_mask.view(B, D, D)
+
+    @torch.no_grad()
     def splat(self, cell_idx, pc_feat, pc_sem=None, want_bf16=False):
         """Pools (B,P,C) fp32 features (and (B,P,S) fp64 labels) into the D*D cells given the cell index."""
         ncell = self.map_dim * self.map_dim

@@ -179,3 +179,29 @@ def build_sap_fusion(gmap_vpids, gmap_visited_masks, last_cand_vpids, G, Kc, dev
     F[:, 0, :] = 0.0
     F[:, 0, 0] = 1.0
     return F
+
+
+# ------------------------------------------------------------------ reference-named helpers (drop-in surface)
+def extend_neg_masks(masks, dtype=None):
+    """(N, L) bool -> (N, 1, 1, L) additive mask, 0 where valid and -10000 where padded
+    (pretrain_src/model/ops.py:25-34, map_nav_src/models/ops.py:25-34).  The kernels take the (N, L) form
+    (`neg_key_mask`); this is the reference's broadcastable shape for callers that build masks themselves."""
+    return neg_key_mask(masks).to(dtype or torch.float32)[:, None, None, :]
+
+
+def pad_tensors_wgrad(tensors, lens=None):
+    """B x [T_i, ...] -> (B, max T, ...) zero-padded, gradients flow to the inputs (pretrain_src/model/ops.py:46-68,
+    map_nav_src/models/ops.py:46-68; used by map_nav_src/r2r/agent.py:250, reverie/agent_obj.py:254,345).
+    One allocation + B slice copies instead of a cat per sample."""
+    if lens is None:
+        lens = [t.size(0) for t in tensors]
+    max_len = max(lens)
+    out = tensors[0].new_zeros((len(tensors), max_len) + tuple(tensors[0].shape[1:]))
+    if any(t.requires_grad for t in tensors):
+        parts = []
+        for t, n in zip(tensors, lens):
+            parts.append(t if n == max_len else torch.cat([t, t.new_zeros((max_len - n,) + tuple(t.shape[1:]))], 0))
+        return torch.stack(parts, 0)
+    for i, (t, n) in enumerate(zip(tensors, lens)):
+        out[i, :n] = t[:n]
+    return out
