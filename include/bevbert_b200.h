@@ -63,6 +63,15 @@ typedef struct bb_gemm_args {
 } bb_gemm_args;
 
 int bb_gemm_bf16(const bb_gemm_args* args, void* stream);
+/* High-precision VERIFICATION arm (csrc/gemm_f32.cu + the float instantiations of every row kernel): after
+ * bb_set_act_f32(1) every "bf16" activation pointer of this header (GEMM operands / outputs, row-kernel inputs and
+ * outputs, P / dS of the unfused attention sequence) is interpreted as fp32 and bb_gemm_bf16 runs an fp32 CUDA-core
+ * GEMM with the same epilogue semantics.  The fused attention cores (bb_flash_*, bb_attn_scores) and the native
+ * sub-layer executors (bb_attn_*, bb_ffn_*, bb_pano_*) are bf16-only: the caller composes the unfused kernels instead.
+ * Used by the parity tests to hold the model to 1e-3 against the fp32 oracle (north_star); process-wide, default 0.
+ * Returns the previous mode. */
+int bb_set_act_f32(int on);
+int bb_get_act_f32(void);
 /* Optional measurement hook (bench.py roofline): while enabled, every bb_gemm_bf16 launch is bracketed by a pair
  * of CUDA events on its stream.  bb_gemm_profile(1) resets and starts, (0) stops; _count() = launches recorded;
  * _read(i, &ms, dims) synchronises on launch i and returns its duration and (M, N, K, batches, a_mn, b_mn). */

@@ -106,7 +106,7 @@ class WeightCache:
         return ent.epoch == self.epoch and ent.ver == tuple(p._version for p in ent.params)
 
     def get(self, *params, pad_k: int = 0, pad_n: int = 0):
-        key = tuple(p.data_ptr() for p in params) + (pad_k, pad_n)
+        key = tuple(p.data_ptr() for p in params) + (pad_k, pad_n, K.act_dtype())
         ent = self._c.get(key)
         if ent is not None and self._fresh(ent):
             return ent.buf
@@ -324,7 +324,7 @@ def attn_core_fwd(st, q, ldq, k, ldk, v, ldv, B, H, nq, nk, dh, kmask, bias, dro
     """softmax(Q K^T / sqrt(dh) + kmask + bias) V for every (sample, head).  q/k/v are views whose first
     element is (sample 0, row 0, head 0, dim 0); rows are ld* apart, heads dh apart.  -> ctx (B*nq, H*dh)."""
     ldp = _round8(nk)
-    if K.FLASH and dh == 64:
+    if K.use_flash() and dh == 64:
         ctx, lse = K.flash_fwd(q, k, v, B, H, nq, nk, ldq, ldk, ldv, kmask, bias, drop)
         st.update(lse=lse, fctx=ctx, geo=(B, H, nq, nk, dh, ldp), adrop=drop, amask=(kmask, bias))
         return ctx.view(B * nq, H * dh)

@@ -738,9 +738,15 @@ static int two_cta_mode() {
 
 }  // namespace bb
 
+namespace bb {
+bool act_f32();                                                    // gemm_f32.cu
+int gemm_f32_launch(const bb_gemm_args* a, cudaStream_t stream);   // fp32 verification arm
+}  // namespace bb
+
 extern "C" int bb_gemm_bf16(const bb_gemm_args* a, void* stream_) {
   using namespace bb;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (act_f32()) return gemm_f32_launch(a, stream);
   if (!a || !a->A || !a->B || !a->D) return set_error("bb_gemm_bf16: null argument");
   if (a->M <= 0 || a->N <= 0 || a->K <= 0) return set_error("bb_gemm_bf16: M, N, K must be positive");
   if (int e = init_device_info()) return e;

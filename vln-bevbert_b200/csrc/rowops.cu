@@ -14,6 +14,15 @@
 namespace bb {
 
 typedef __nv_bfloat16 bf16;
+bool act_f32();   // gemm_f32.cu: fp32-activation verification mode (bb_set_act_f32)
+
+// Activation storage type T: bf16 in the product, float in the high-precision verification arm (every kernel that
+// reads or writes activations is instantiated for both; the C entry points pick by bb::act_f32()).
+__device__ __forceinline__ float tof(bf16 v) { return __bfloat162float(v); }
+__device__ __forceinline__ float tof(float v) { return v; }
+template <typename T> __device__ __forceinline__ T fromf(float v);
+template <> __device__ __forceinline__ bf16 fromf<bf16>(float v) { return __float2bfloat16(v); }
+template <> __device__ __forceinline__ float fromf<float>(float v) { return v; }
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -53,7 +62,8 @@ __device__ __forceinline__ void store8(float* p, const float (&v)[8]) {
 }
 
 // ------------------------------------------------------------------------------------- casts
-__global__ void cast_f32_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, long long n, uint64_t seed,
+template <typename T>
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ src, T* __restrict__ dst, long long n, uint64_t seed,
                                      uint32_t thresh, float scale) {
   bb::pdl_wait();
   bb::pdl_trigger();
@@ -71,12 +81,13 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, bf16* __rest
       for (long long j = i; j < n; ++j) {
         float v = src[j];
         if (thresh) v = drop_keep(seed, j, thresh) ? v * scale : 0.f;
-        dst[j] = __float2bfloat16(v);
+        dst[j] = fromf<T>(v);
       }
     }
   }
 }
-__global__ void cast_bf16_f32_kernel(const bf16* __restrict__ src, float* __restrict__ dst, long long n) {
+template <typename T>
+__global__ void cast_bf16_f32_kernel(const T* __restrict__ src, float* __restrict__ dst, long long n) {
   bb::pdl_wait();
   bb::pdl_trigger();
   const long long stride = (long long)gridDim.x * blockDim.x * 8;
@@ -86,11 +97,12 @@ __global__ void cast_bf16_f32_kernel(const bf16* __restrict__ src, float* __rest
       load8(src + i, v);
       store8(dst + i, v);
     } else {
-      for (long long j = i; j < n; ++j) dst[j] = __bfloat162float(src[j]);
+      for (long long j = i; j < n; ++j) dst[j] = tof(src[j]);
     }
   }
 }
-__global__ void add_bf16_kernel(const bf16* __restrict__ a, const bf16* __restrict__ b, bf16* __restrict__ out,
+template <typename T>
+__global__ void add_bf16_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ out,
                                 long long n) {
   bb::pdl_wait();
   bb::pdl_trigger();
@@ -104,11 +116,12 @@ __global__ void add_bf16_kernel(const bf16* __restrict__ a, const bf16* __restri
       for (int j = 0; j < 8; ++j) x[j] += y[j];
       store8(out + i, x);
     } else {
-      for (long long j = i; j < n; ++j) out[j] = __float2bfloat16(__bfloat162float(a[j]) + __bfloat162float(b[j]));
+      for (long long j = i; j < n; ++j) out[j] = fromf<T>(tof(a[j]) + tof(b[j]));
     }
   }
 }
-__global__ void dropout_bf16_kernel(const bf16* __restrict__ src, bf16* __restrict__ dst, long long n, uint64_t seed,
+template <typename T>
+__global__ void dropout_bf16_kernel(const T* __restrict__ src, T* __restrict__ dst, long long n, uint64_t seed,
                                     uint32_t thresh, float scale) {
   bb::pdl_wait();
   bb::pdl_trigger();
@@ -122,12 +135,13 @@ __global__ void dropout_bf16_kernel(const bf16* __restrict__ src, bf16* __restri
       store8(dst + i, v);
     } else {
       for (long long j = i; j < n; ++j)
-        dst[j] = __float2bfloat16(drop_keep(seed, j, thresh) ? __bfloat162float(src[j]) * scale : 0.f);
+        dst[j] = fromf<T>(drop_keep(seed, j, thresh) ? tof(src[j]) * scale : 0.f);
     }
   }
 }
-__global__ void act_bwd_bf16_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ aux, int mode,
-                                    bf16* __restrict__ out, long long n) {
+template <typename T>
+__global__ void act_bwd_bf16_kernel(const T* __restrict__ dy, const T* __restrict__ aux, int mode,
+                                    T* __restrict__ out, long long n) {
   bb::pdl_wait();
   bb::pdl_trigger();
   const long long stride = (long long)gridDim.x * blockDim.x * 8;
@@ -141,16 +155,17 @@ __global__ void act_bwd_bf16_kernel(const bf16* __restrict__ dy, const bf16* __r
       store8(out + i, g);
     } else {
       for (long long j = i; j < n; ++j) {
-        const float a = __bfloat162float(aux[j]), g = __bfloat162float(dy[j]);
-        out[j] = __float2bfloat16((mode == 1) ? g * dgelu_erf(a) : (a > 0.f ? g : 0.f));
+        const float a = tof(aux[j]), g = tof(dy[j]);
+        out[j] = fromf<T>((mode == 1) ? g * dgelu_erf(a) : (a > 0.f ? g : 0.f));
       }
     }
   }
 }
 // out = a (+ b) (+ table[idx[r]]) (+ vec)
-__global__ void add_rows_kernel(const bf16* __restrict__ a, const bf16* __restrict__ b, const float* __restrict__ table,
+template <typename T>
+__global__ void add_rows_kernel(const T* __restrict__ a, const T* __restrict__ b, const float* __restrict__ table,
                                 const int64_t* __restrict__ idx, const float* __restrict__ vec, long long rows, int H,
-                                bf16* __restrict__ out) {
+                                T* __restrict__ out) {
   bb::pdl_wait();
   bb::pdl_trigger();
   const int h8 = H / 8;
@@ -180,17 +195,19 @@ __global__ void add_rows_kernel(const bf16* __restrict__ a, const bf16* __restri
   }
   store8(out + r * H + c, v);
 }
-__global__ void scale_rows_bf16_kernel(bf16* __restrict__ x, const float* __restrict__ g, long long rows, long long ld) {
+template <typename T>
+__global__ void scale_rows_bf16_kernel(T* __restrict__ x, const float* __restrict__ g, long long rows, long long ld) {
   bb::pdl_wait();
   bb::pdl_trigger();
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= rows * ld) return;
-  x[i] = __float2bfloat16(__bfloat162float(x[i]) * g[i / ld]);
+  x[i] = fromf<T>(tof(x[i]) * g[i / ld]);
 }
 // one warp per segment; lanes stride over H in 8-wide chunks
-__global__ void segment_wsum_kernel(const bf16* __restrict__ src, const int32_t* __restrict__ seg_off,
+template <typename T>
+__global__ void segment_wsum_kernel(const T* __restrict__ src, const int32_t* __restrict__ seg_off,
                                     const int32_t* __restrict__ idx, const float* __restrict__ w, long long nseg, int H,
-                                    bf16* __restrict__ out) {
+                                    T* __restrict__ out) {
   bb::pdl_wait();
   bb::pdl_trigger();
   const int lane = threadIdx.x & 31;
@@ -211,7 +228,8 @@ __global__ void segment_wsum_kernel(const bf16* __restrict__ src, const int32_t*
     store8(out + s * H + c, acc);
   }
 }
-__global__ void segment_wsum_bwd_kernel(const bf16* __restrict__ dout, const int32_t* __restrict__ seg_off,
+template <typename T>
+__global__ void segment_wsum_bwd_kernel(const T* __restrict__ dout, const int32_t* __restrict__ seg_off,
                                         const int32_t* __restrict__ idx, const float* __restrict__ w, long long nseg,
                                         int H, float* __restrict__ dsrc) {
   bb::pdl_wait();
@@ -231,24 +249,25 @@ __global__ void segment_wsum_bwd_kernel(const bf16* __restrict__ dout, const int
     }
   }
 }
-__global__ void axpy_f32_from_bf16_kernel(const bf16* __restrict__ x, float* __restrict__ y, long long n) {
+template <typename T>
+__global__ void axpy_f32_from_bf16_kernel(const T* __restrict__ x, float* __restrict__ y, long long n) {
   bb::pdl_wait();
   bb::pdl_trigger();
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += stride)
-    y[i] += __bfloat162float(x[i]);
+    y[i] += tof(x[i]);
 }
 
 // ------------------------------------------------------------------------------------- LayerNorm
 constexpr int LN_MAXCH = 4;  // 4 chunks of 256 columns -> H <= 1024
 constexpr int LN_WARPS = 8;
 
-template <typename XT>
+template <typename XT, typename T>
 __global__ void __launch_bounds__(LN_WARPS * 32)
-layernorm_fwd_kernel(const XT* __restrict__ x, const bf16* __restrict__ res, const float* __restrict__ gamma,
+layernorm_fwd_kernel(const XT* __restrict__ x, const T* __restrict__ res, const float* __restrict__ gamma,
                      const float* __restrict__ beta, float eps, long long rows, int H, uint64_t seed_in,
                      uint32_t thresh_in, float scale_in, uint64_t seed_out, uint32_t thresh_out, float scale_out,
-                     bf16* __restrict__ y, float* __restrict__ y_f32, float* __restrict__ mean_out,
+                     T* __restrict__ y, float* __restrict__ y_f32, float* __restrict__ mean_out,
                      float* __restrict__ rstd_out) {
   bb::pdl_wait();
   bb::pdl_trigger();
@@ -316,13 +335,13 @@ layernorm_fwd_kernel(const XT* __restrict__ x, const bf16* __restrict__ res, con
 
 // Backward. Grid-stride over rows (one warp per row); each lane keeps per-column dgamma/dbeta partials,
 // reduced through shared memory and flushed with one atomicAdd per column per block.
-template <typename DYT, typename XT, typename DXT>
+template <typename DYT, typename XT, typename DXT, typename T>
 __global__ void __launch_bounds__(LN_WARPS * 32)
-layernorm_bwd_kernel(const DYT* __restrict__ dy, const XT* __restrict__ x, const bf16* __restrict__ res,
+layernorm_bwd_kernel(const DYT* __restrict__ dy, const XT* __restrict__ x, const T* __restrict__ res,
                      const float* __restrict__ gamma, const float* __restrict__ mean_in,
                      const float* __restrict__ rstd_in, long long rows, int H, uint64_t seed_in, uint32_t thresh_in,
                      float scale_in, uint64_t seed_out, uint32_t thresh_out, float scale_out, DXT* __restrict__ dx,
-                     bf16* __restrict__ dres, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                     T* __restrict__ dres, float* __restrict__ dgamma, float* __restrict__ dbeta,
                      float* __restrict__ dxsum) {
   bb::pdl_wait();
   bb::pdl_trigger();
@@ -421,8 +440,9 @@ layernorm_bwd_kernel(const DYT* __restrict__ dy, const XT* __restrict__ x, const
 }
 
 // ------------------------------------------------------------------------------------- column sums
+template <typename T>
 __global__ void __launch_bounds__(256)
-colsum_bf16_kernel(const bf16* __restrict__ x, long long rows, int N, long long ld, float* __restrict__ out) {
+colsum_bf16_kernel(const T* __restrict__ x, long long rows, int N, long long ld, float* __restrict__ out) {
   bb::pdl_wait();
   bb::pdl_trigger();
   // blockDim = (32, 8): 32 lanes x 8 columns each = 256 columns per block in x; rows strided over y and grid.y
@@ -441,7 +461,7 @@ colsum_bf16_kernel(const bf16* __restrict__ x, long long rows, int N, long long 
         for (int j = 0; j < 8; ++j) acc[j] += v[j];
       } else {
         for (int j = 0; j < 8; ++j)
-          if (col + j < N) acc[j] += __bfloat162float(x[r * ld + col + j]);
+          if (col + j < N) acc[j] += tof(x[r * ld + col + j]);
       }
     }
   }
@@ -457,11 +477,11 @@ colsum_bf16_kernel(const bf16* __restrict__ x, long long rows, int N, long long 
 }
 
 // ------------------------------------------------------------------------------------- softmax
-template <int MAXE>
+template <int MAXE, typename T>
 __global__ void __launch_bounds__(256)
 softmax_fwd_kernel(const float* __restrict__ scores, const float* __restrict__ kmask, const float* __restrict__ bias,
                    long long nrows, int H, int nq, int nk, int ld, uint64_t seed, uint32_t thresh, float scale,
-                   bf16* __restrict__ probs, bf16* __restrict__ probs_drop) {
+                   T* __restrict__ probs, T* __restrict__ probs_drop) {
   bb::pdl_wait();
   bb::pdl_trigger();
   const int lane = threadIdx.x & 31;
@@ -497,27 +517,27 @@ softmax_fwd_kernel(const float* __restrict__ scores, const float* __restrict__ k
   }
   sum = warp_sum(sum);
   const float inv = 1.0f / sum;
-  bf16* p = probs + row * ld;
-  bf16* pd = probs_drop ? probs_drop + row * ld : nullptr;
+  T* p = probs + row * ld;
+  T* pd = probs_drop ? probs_drop + row * ld : nullptr;
 #pragma unroll
   for (int e = 0; e < MAXE; ++e) {
     const int k = e * 32 + lane;
     if (k < ld) {
       const float pr = (k < nk) ? v[e] * inv : 0.f;
-      p[k] = __float2bfloat16(pr);
+      p[k] = fromf<T>(pr);
       if (pd) {
         float t = pr;
         if (thresh) t = drop_keep(seed, row * ld + k, thresh) ? pr * scale : 0.f;
-        pd[k] = __float2bfloat16(t);
+        pd[k] = fromf<T>(t);
       }
     }
   }
 }
 
-template <int MAXE>
+template <int MAXE, typename T>
 __global__ void __launch_bounds__(256)
-softmax_bwd_kernel(const bf16* __restrict__ probs, const float* __restrict__ dprobs, long long nrows, int H, int nq,
-                   int nk, int ld, uint64_t seed, uint32_t thresh, float scale, float out_scale, bf16* __restrict__ ds,
+softmax_bwd_kernel(const T* __restrict__ probs, const float* __restrict__ dprobs, long long nrows, int H, int nq,
+                   int nk, int ld, uint64_t seed, uint32_t thresh, float scale, float out_scale, T* __restrict__ ds,
                    float* __restrict__ dbias) {
   bb::pdl_wait();
   bb::pdl_trigger();
@@ -526,7 +546,7 @@ softmax_bwd_kernel(const bf16* __restrict__ probs, const float* __restrict__ dpr
   if (row >= nrows) return;
   const int q = row % nq;
   const long long b = row / ((long long)nq * H);
-  const bf16* p = probs + row * ld;
+  const T* p = probs + row * ld;
   const float* dp = dprobs + row * ld;
   float pv[MAXE], g[MAXE];
   float dot = 0.f;
@@ -536,7 +556,7 @@ softmax_bwd_kernel(const bf16* __restrict__ probs, const float* __restrict__ dpr
     pv[e] = 0.f;
     g[e] = 0.f;
     if (k < nk) {
-      pv[e] = __bfloat162float(p[k]);
+      pv[e] = tof(p[k]);
       float t = dp[k];
       if (thresh) t = drop_keep(seed, row * ld + k, thresh) ? t * scale : 0.f;
       g[e] = t;
@@ -544,14 +564,14 @@ softmax_bwd_kernel(const bf16* __restrict__ probs, const float* __restrict__ dpr
     }
   }
   dot = warp_sum(dot);
-  bf16* o = ds + row * ld;
+  T* o = ds + row * ld;
   float* db = dbias ? dbias + (b * nq + q) * nk : nullptr;
 #pragma unroll
   for (int e = 0; e < MAXE; ++e) {
     const int k = e * 32 + lane;
     if (k < ld) {
       const float d = (k < nk) ? pv[e] * (g[e] - dot) : 0.f;
-      o[k] = __float2bfloat16(d * out_scale);
+      o[k] = fromf<T>(d * out_scale);
       if (db && k < nk) atomicAdd(db + k, d);
     }
   }
@@ -597,8 +617,9 @@ __global__ void embed_scatter_grad_kernel(const int64_t* __restrict__ ids, const
 }
 
 // ------------------------------------------------------------------------------------- gather / scatter rows
-__global__ void gather_rows_bf16_kernel(const bf16* __restrict__ in, const int64_t* __restrict__ idx, long long nout,
-                                        int H, bf16* __restrict__ out) {
+template <typename T>
+__global__ void gather_rows_bf16_kernel(const T* __restrict__ in, const int64_t* __restrict__ idx, long long nout,
+                                        int H, T* __restrict__ out) {
   bb::pdl_wait();
   bb::pdl_trigger();
   const int h8 = H / 8;
@@ -607,11 +628,12 @@ __global__ void gather_rows_bf16_kernel(const bf16* __restrict__ in, const int64
   const long long r = i / h8;
   const int c = (i % h8) * 8;
   const int64_t src = idx[r];
-  uint4 v = make_uint4(0, 0, 0, 0);
-  if (src >= 0) v = __ldg(reinterpret_cast<const uint4*>(in + src * H + c));
-  *reinterpret_cast<uint4*>(out + r * H + c) = v;
+  float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (src >= 0) load8(in + src * H + c, v);
+  store8(out + r * H + c, v);
 }
-__global__ void scatter_add_rows_kernel(const bf16* __restrict__ in, const int64_t* __restrict__ idx, long long nin,
+template <typename T>
+__global__ void scatter_add_rows_kernel(const T* __restrict__ in, const int64_t* __restrict__ idx, long long nin,
                                         int H, float* __restrict__ out) {
   bb::pdl_wait();
   bb::pdl_trigger();
@@ -620,13 +642,14 @@ __global__ void scatter_add_rows_kernel(const bf16* __restrict__ in, const int64
   const long long r = i / H;
   const int c = i % H;
   const int64_t dst = idx[r];
-  if (dst >= 0) atomicAdd(out + dst * H + c, __bfloat162float(in[i]));
+  if (dst >= 0) atomicAdd(out + dst * H + c, tof(in[i]));
 }
 
 // ------------------------------------------------------------------------------------- softmax cross entropy
+template <typename T>
 __global__ void __launch_bounds__(256)
 softmax_xent_kernel(const float* __restrict__ logits, const int64_t* __restrict__ labels, int V, long long ld,
-                    float* __restrict__ loss, const float* __restrict__ gscale, bf16* __restrict__ dlogits) {
+                    float* __restrict__ loss, const float* __restrict__ gscale, T* __restrict__ dlogits) {
   bb::pdl_wait();
   bb::pdl_trigger();
   __shared__ float red[8];
@@ -665,11 +688,11 @@ softmax_xent_kernel(const float* __restrict__ logits, const int64_t* __restrict_
   if (dlogits) {
     const float gs = valid ? (gscale ? gscale[row] : 1.f) : 0.f;
     const float inv = 1.0f / s;
-    bf16* d = dlogits + row * ld;
+    T* d = dlogits + row * ld;
     for (int i = threadIdx.x; i < ld; i += 256) {
       float g = 0.f;
       if (i < V) g = (__expf(x[i] - mx) * inv - (i == lab ? 1.f : 0.f)) * gs;
-      d[i] = __float2bfloat16(g);
+      d[i] = fromf<T>(g);
     }
   }
 }
@@ -685,19 +708,30 @@ static inline unsigned grid1d(long long n, int per_block, int cap = 148 * 16) {
 
 using namespace bb;
 #define STREAM ((cudaStream_t)stream)
+// run the statement with T = float in the fp32 verification mode, T = bf16 otherwise
+#define ACT_T(...)              \
+  do {                          \
+    if (bb::act_f32()) {        \
+      typedef float T;          \
+      __VA_ARGS__;              \
+    } else {                    \
+      typedef bf16 T;           \
+      __VA_ARGS__;              \
+    }                           \
+  } while (0)
 
 extern "C" int bb_cast_f32_bf16(const float* src, void* dst, int64_t n, uint64_t seed, uint32_t thresh, float scale,
                                 void* stream) {
   if (n <= 0) return 0;
   if (((uintptr_t)src & 15) || ((uintptr_t)dst & 15)) return set_error("bb_cast_f32_bf16: pointers must be 16B aligned");
-  bb::launch_pdl(cast_f32_bf16_kernel, grid1d(n, 256 * 8), 256, 0, STREAM, src, (bf16*)dst, n, seed, thresh, scale);
+  ACT_T(bb::launch_pdl(cast_f32_bf16_kernel<T>, grid1d(n, 256 * 8), 256, 0, STREAM, src, (T*)dst, n, seed, thresh, scale));
   count_launch();
   return check_launch("cast_f32_bf16_kernel");
 }
 extern "C" int bb_cast_bf16_f32(const void* src, float* dst, int64_t n, void* stream) {
   if (n <= 0) return 0;
   if (((uintptr_t)src & 15) || ((uintptr_t)dst & 15)) return set_error("bb_cast_bf16_f32: pointers must be 16B aligned");
-  bb::launch_pdl(cast_bf16_f32_kernel, grid1d(n, 256 * 8), 256, 0, STREAM, (const bf16*)src, dst, n);
+  ACT_T(bb::launch_pdl(cast_bf16_f32_kernel<T>, grid1d(n, 256 * 8), 256, 0, STREAM, (const T*)src, dst, n));
   count_launch();
   return check_launch("cast_bf16_f32_kernel");
 }
@@ -705,7 +739,7 @@ extern "C" int bb_add_bf16(const void* a, const void* b, void* out, int64_t n, v
   if (n <= 0) return 0;
   if (((uintptr_t)a & 15) || ((uintptr_t)b & 15) || ((uintptr_t)out & 15))
     return set_error("bb_add_bf16: pointers must be 16B aligned");
-  bb::launch_pdl(add_bf16_kernel, grid1d(n, 256 * 8), 256, 0, STREAM, (const bf16*)a, (const bf16*)b, (bf16*)out, n);
+  ACT_T(bb::launch_pdl(add_bf16_kernel<T>, grid1d(n, 256 * 8), 256, 0, STREAM, (const T*)a, (const T*)b, (T*)out, n));
   count_launch();
   return check_launch("add_bf16_kernel");
 }
@@ -713,7 +747,7 @@ extern "C" int bb_dropout_bf16(const void* src, void* dst, int64_t n, uint64_t s
                                void* stream) {
   if (n <= 0) return 0;
   if (((uintptr_t)src & 15) || ((uintptr_t)dst & 15)) return set_error("bb_dropout_bf16: pointers must be 16B aligned");
-  bb::launch_pdl(dropout_bf16_kernel, grid1d(n, 256 * 8), 256, 0, STREAM, (const bf16*)src, (bf16*)dst, n, seed, thresh, scale);
+  ACT_T(bb::launch_pdl(dropout_bf16_kernel<T>, grid1d(n, 256 * 8), 256, 0, STREAM, (const T*)src, (T*)dst, n, seed, thresh, scale));
   count_launch();
   return check_launch("dropout_bf16_kernel");
 }
@@ -722,7 +756,7 @@ extern "C" int bb_act_bwd_bf16(const void* dy, const void* aux, int mode, void* 
   if (mode != 1 && mode != 2) return set_error("bb_act_bwd_bf16: mode must be 1 (gelu) or 2 (relu)");
   if (((uintptr_t)dy & 15) || ((uintptr_t)aux & 15) || ((uintptr_t)out & 15))
     return set_error("bb_act_bwd_bf16: pointers must be 16B aligned");
-  bb::launch_pdl(act_bwd_bf16_kernel, grid1d(n, 256 * 8), 256, 0, STREAM, (const bf16*)dy, (const bf16*)aux, mode, (bf16*)out, n);
+  ACT_T(bb::launch_pdl(act_bwd_bf16_kernel<T>, grid1d(n, 256 * 8), 256, 0, STREAM, (const T*)dy, (const T*)aux, mode, (T*)out, n));
   count_launch();
   return check_launch("act_bwd_bf16_kernel");
 }
@@ -732,15 +766,15 @@ extern "C" int bb_add_rows(const void* a, const void* b, const float* table, con
   if (H % 8 != 0) return set_error("bb_add_rows: H must be a multiple of 8");
   if (table && !idx) return set_error("bb_add_rows: table needs idx");
   const long long n = rows * (H / 8);
-  bb::launch_pdl(add_rows_kernel, (unsigned)((n + 255) / 256), 256, 0, STREAM, (const bf16*)a, (const bf16*)b, table, idx, vec,
-                                                                   rows, H, (bf16*)out);
+  ACT_T(bb::launch_pdl(add_rows_kernel<T>, (unsigned)((n + 255) / 256), 256, 0, STREAM, (const T*)a, (const T*)b, table, idx, vec,
+                                                                   rows, H, (T*)out));
   count_launch();
   return check_launch("add_rows_kernel");
 }
 extern "C" int bb_scale_rows_bf16(void* x, const float* g, int64_t rows, int64_t ld, void* stream) {
   if (rows <= 0) return 0;
   const long long n = rows * ld;
-  bb::launch_pdl(scale_rows_bf16_kernel, (unsigned)((n + 255) / 256), 256, 0, STREAM, (bf16*)x, g, rows, ld);
+  ACT_T(bb::launch_pdl(scale_rows_bf16_kernel<T>, (unsigned)((n + 255) / 256), 256, 0, STREAM, (T*)x, g, rows, ld));
   count_launch();
   return check_launch("scale_rows_bf16_kernel");
 }
@@ -748,8 +782,8 @@ extern "C" int bb_segment_wsum(const void* src, const int32_t* seg_off, const in
                                int64_t nseg, int H, void* out, void* stream) {
   if (nseg <= 0) return 0;
   if (H % 8 != 0) return set_error("bb_segment_wsum: H must be a multiple of 8");
-  bb::launch_pdl(segment_wsum_kernel, (unsigned)((nseg + 7) / 8), 256, 0, STREAM, (const bf16*)src, seg_off, idx, w, nseg, H,
-                                                                      (bf16*)out);
+  ACT_T(bb::launch_pdl(segment_wsum_kernel<T>, (unsigned)((nseg + 7) / 8), 256, 0, STREAM, (const T*)src, seg_off, idx, w, nseg, H,
+                                                                      (T*)out));
   count_launch();
   return check_launch("segment_wsum_kernel");
 }
@@ -757,14 +791,14 @@ extern "C" int bb_segment_wsum_bwd(const void* dout, const int32_t* seg_off, con
                                    int64_t nseg, int H, float* dsrc_f32, void* stream) {
   if (nseg <= 0) return 0;
   if (H % 8 != 0) return set_error("bb_segment_wsum_bwd: H must be a multiple of 8");
-  bb::launch_pdl(segment_wsum_bwd_kernel, (unsigned)((nseg + 7) / 8), 256, 0, STREAM, (const bf16*)dout, seg_off, idx, w, nseg, H,
-                                                                          dsrc_f32);
+  ACT_T(bb::launch_pdl(segment_wsum_bwd_kernel<T>, (unsigned)((nseg + 7) / 8), 256, 0, STREAM, (const T*)dout, seg_off, idx, w, nseg, H,
+                                                                          dsrc_f32));
   count_launch();
   return check_launch("segment_wsum_bwd_kernel");
 }
 extern "C" int bb_axpy_f32_from_bf16(const void* x, float* y, int64_t n, void* stream) {
   if (n <= 0) return 0;
-  bb::launch_pdl(axpy_f32_from_bf16_kernel, grid1d(n, 256), 256, 0, STREAM, (const bf16*)x, y, n);
+  ACT_T(bb::launch_pdl(axpy_f32_from_bf16_kernel<T>, grid1d(n, 256), 256, 0, STREAM, (const T*)x, y, n));
   count_launch();
   return check_launch("axpy_f32_from_bf16_kernel");
 }
@@ -777,13 +811,13 @@ extern "C" int bb_layernorm_fwd(const void* x, int x_f32, const void* residual, 
   if (H % 8 != 0 || H > LN_MAXCH * 256) return set_error("bb_layernorm_fwd: H must be a multiple of 8 and <= 1024");
   const unsigned grid = (unsigned)((rows + LN_WARPS - 1) / LN_WARPS);
   if (x_f32)
-    bb::launch_pdl(layernorm_fwd_kernel<float>, grid, LN_WARPS * 32, 0, STREAM, 
-        (const float*)x, (const bf16*)residual, gamma, beta, eps, rows, H, seed_in, thresh_in, scale_in, seed_out,
-        thresh_out, scale_out, (bf16*)y, y_f32, mean, rstd);
+    ACT_T(bb::launch_pdl(layernorm_fwd_kernel<float, T>, grid, LN_WARPS * 32, 0, STREAM, 
+        (const float*)x, (const T*)residual, gamma, beta, eps, rows, H, seed_in, thresh_in, scale_in, seed_out,
+        thresh_out, scale_out, (T*)y, y_f32, mean, rstd));
   else
-    bb::launch_pdl(layernorm_fwd_kernel<bf16>, grid, LN_WARPS * 32, 0, STREAM, 
-        (const bf16*)x, (const bf16*)residual, gamma, beta, eps, rows, H, seed_in, thresh_in, scale_in, seed_out,
-        thresh_out, scale_out, (bf16*)y, y_f32, mean, rstd);
+    ACT_T(bb::launch_pdl(layernorm_fwd_kernel<bf16, T>, grid, LN_WARPS * 32, 0, STREAM, 
+        (const bf16*)x, (const T*)residual, gamma, beta, eps, rows, H, seed_in, thresh_in, scale_in, seed_out,
+        thresh_out, scale_out, (T*)y, y_f32, mean, rstd));
   count_launch();
   return check_launch("layernorm_fwd_kernel");
 }
@@ -799,28 +833,26 @@ extern "C" int bb_layernorm_bwd(const void* dy, int dy_f32, const void* x, int x
   if (g > 148 * 2) g = 148 * 2;
   const unsigned grid = (unsigned)g;
   const size_t ln_smem = (size_t)3 * LN_WARPS * H * sizeof(float);
-  {
-    static bool attr_done = false;
-    if (!attr_done) {
-      cudaFuncSetAttribute(layernorm_bwd_kernel<bf16, bf16, bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304);
-      cudaFuncSetAttribute(layernorm_bwd_kernel<bf16, float, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304);
-      cudaFuncSetAttribute(layernorm_bwd_kernel<float, bf16, bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304);
-      cudaFuncSetAttribute(layernorm_bwd_kernel<float, float, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304);
-      cudaFuncSetAttribute(layernorm_bwd_kernel<bf16, bf16, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304);
-      cudaFuncSetAttribute(layernorm_bwd_kernel<bf16, float, bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304);
-      attr_done = true;
-    }
-  }
-#define LN_BWD(DYT, XT, DXT)                                                                                        \
-  bb::launch_pdl(layernorm_bwd_kernel<DYT, XT, DXT>, grid, LN_WARPS * 32, ln_smem, STREAM,                                      \
-      (const DYT*)dy, (const XT*)x, (const bf16*)residual, gamma, mean, rstd, rows, H, seed_in, thresh_in, scale_in, \
-      seed_out, thresh_out, scale_out, (DXT*)dx, (bf16*)dres, dgamma, dbeta, dxsum)
-  if (!dy_f32 && !x_f32 && !dx_f32) LN_BWD(bf16, bf16, bf16);
-  else if (!dy_f32 && x_f32 && dx_f32) LN_BWD(bf16, float, float);
-  else if (dy_f32 && !x_f32 && !dx_f32) LN_BWD(float, bf16, bf16);
-  else if (dy_f32 && x_f32 && dx_f32) LN_BWD(float, float, float);
-  else if (!dy_f32 && !x_f32 && dx_f32) LN_BWD(bf16, bf16, float);
-  else if (!dy_f32 && x_f32 && !dx_f32) LN_BWD(bf16, float, bf16);
+#define LN_BWD(DYT, XT, DXT, AT)                                                                                    \
+  do {                                                                                                              \
+    static bool attr_done = false;                                                                                  \
+    if (!attr_done) {                                                                                               \
+      cudaFuncSetAttribute(layernorm_bwd_kernel<DYT, XT, DXT, AT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304); \
+      attr_done = true;                                                                                             \
+    }                                                                                                               \
+    bb::launch_pdl(layernorm_bwd_kernel<DYT, XT, DXT, AT>, grid, LN_WARPS * 32, ln_smem, STREAM, (const DYT*)dy,    \
+                   (const XT*)x, (const AT*)residual, gamma, mean, rstd, rows, H, seed_in, thresh_in, scale_in,     \
+                   seed_out, thresh_out, scale_out, (DXT*)dx, (AT*)dres, dgamma, dbeta, dxsum);                     \
+  } while (0)
+  if (bb::act_f32()) {
+    if (dy_f32 && x_f32 && dx_f32) LN_BWD(float, float, float, float);
+    else return set_error("bb_layernorm_bwd: the fp32 verification mode needs fp32 dy / x / dx");
+  } else if (!dy_f32 && !x_f32 && !dx_f32) LN_BWD(bf16, bf16, bf16, bf16);
+  else if (!dy_f32 && x_f32 && dx_f32) LN_BWD(bf16, float, float, bf16);
+  else if (dy_f32 && !x_f32 && !dx_f32) LN_BWD(float, bf16, bf16, bf16);
+  else if (dy_f32 && x_f32 && dx_f32) LN_BWD(float, float, float, bf16);
+  else if (!dy_f32 && !x_f32 && dx_f32) LN_BWD(bf16, bf16, float, bf16);
+  else if (!dy_f32 && x_f32 && !dx_f32) LN_BWD(bf16, float, bf16, bf16);
   else return set_error("bb_layernorm_bwd: unsupported dtype combination");
 #undef LN_BWD
   count_launch();
@@ -832,7 +864,7 @@ extern "C" int bb_colsum_bf16(const void* x, int64_t rows, int N, int64_t ld, fl
   long long gy = (rows + 63) / 64;
   if (gy > 64) gy = 64;
   dim3 grid((N + 255) / 256, (unsigned)gy);
-  bb::launch_pdl(colsum_bf16_kernel, grid, dim3(32, 8), 0, STREAM, (const bf16*)x, rows, N, ld, out);
+  ACT_T(bb::launch_pdl(colsum_bf16_kernel<T>, grid, dim3(32, 8), 0, STREAM, (const T*)x, rows, N, ld, out));
   count_launch();
   return check_launch("colsum_bf16_kernel");
 }
@@ -845,14 +877,14 @@ extern "C" int bb_softmax_fwd(const float* scores, const float* kmask, const flo
   if (ld < nk || ld > 1024) return set_error("bb_softmax_fwd: need nk <= ld <= 1024");
   const unsigned grid = (unsigned)((nrows + 7) / 8);
   if (ld <= 128)
-    bb::launch_pdl(softmax_fwd_kernel<4>, grid, 256, 0, STREAM, scores, kmask, bias, nrows, H, nq, nk, ld, seed, thresh, scale,
-                                                    (bf16*)probs, (bf16*)probs_drop);
+    ACT_T(bb::launch_pdl(softmax_fwd_kernel<4, T>, grid, 256, 0, STREAM, scores, kmask, bias, nrows, H, nq, nk, ld, seed, thresh, scale,
+                                                    (T*)probs, (T*)probs_drop));
   else if (ld <= 512)
-    bb::launch_pdl(softmax_fwd_kernel<16>, grid, 256, 0, STREAM, scores, kmask, bias, nrows, H, nq, nk, ld, seed, thresh, scale,
-                                                     (bf16*)probs, (bf16*)probs_drop);
+    ACT_T(bb::launch_pdl(softmax_fwd_kernel<16, T>, grid, 256, 0, STREAM, scores, kmask, bias, nrows, H, nq, nk, ld, seed, thresh, scale,
+                                                     (T*)probs, (T*)probs_drop));
   else
-    bb::launch_pdl(softmax_fwd_kernel<32>, grid, 256, 0, STREAM, scores, kmask, bias, nrows, H, nq, nk, ld, seed, thresh, scale,
-                                                     (bf16*)probs, (bf16*)probs_drop);
+    ACT_T(bb::launch_pdl(softmax_fwd_kernel<32, T>, grid, 256, 0, STREAM, scores, kmask, bias, nrows, H, nq, nk, ld, seed, thresh, scale,
+                                                     (T*)probs, (T*)probs_drop));
   count_launch();
   return check_launch("softmax_fwd_kernel");
 }
@@ -865,14 +897,14 @@ extern "C" int bb_softmax_bwd(const void* probs, const float* dprobs, int nbatch
   if (ld < nk || ld > 1024) return set_error("bb_softmax_bwd: need nk <= ld <= 1024");
   const unsigned grid = (unsigned)((nrows + 7) / 8);
   if (ld <= 128)
-    bb::launch_pdl(softmax_bwd_kernel<4>, grid, 256, 0, STREAM, (const bf16*)probs, dprobs, nrows, H, nq, nk, ld, seed, thresh,
-                                                    scale, out_scale, (bf16*)ds, dbias);
+    ACT_T(bb::launch_pdl(softmax_bwd_kernel<4, T>, grid, 256, 0, STREAM, (const T*)probs, dprobs, nrows, H, nq, nk, ld, seed, thresh,
+                                                    scale, out_scale, (T*)ds, dbias));
   else if (ld <= 512)
-    bb::launch_pdl(softmax_bwd_kernel<16>, grid, 256, 0, STREAM, (const bf16*)probs, dprobs, nrows, H, nq, nk, ld, seed, thresh,
-                                                     scale, out_scale, (bf16*)ds, dbias);
+    ACT_T(bb::launch_pdl(softmax_bwd_kernel<16, T>, grid, 256, 0, STREAM, (const T*)probs, dprobs, nrows, H, nq, nk, ld, seed, thresh,
+                                                     scale, out_scale, (T*)ds, dbias));
   else
-    bb::launch_pdl(softmax_bwd_kernel<32>, grid, 256, 0, STREAM, (const bf16*)probs, dprobs, nrows, H, nq, nk, ld, seed, thresh,
-                                                     scale, out_scale, (bf16*)ds, dbias);
+    ACT_T(bb::launch_pdl(softmax_bwd_kernel<32, T>, grid, 256, 0, STREAM, (const T*)probs, dprobs, nrows, H, nq, nk, ld, seed, thresh,
+                                                     scale, out_scale, (T*)ds, dbias));
   count_launch();
   return check_launch("softmax_bwd_kernel");
 }
@@ -900,7 +932,7 @@ extern "C" int bb_gather_rows_bf16(const void* in, const int64_t* idx, int64_t n
   if (nout <= 0) return 0;
   if (H % 8 != 0) return set_error("bb_gather_rows_bf16: H must be a multiple of 8");
   const long long n = nout * (H / 8);
-  bb::launch_pdl(gather_rows_bf16_kernel, (unsigned)((n + 255) / 256), 256, 0, STREAM, (const bf16*)in, idx, nout, H, (bf16*)out);
+  ACT_T(bb::launch_pdl(gather_rows_bf16_kernel<T>, (unsigned)((n + 255) / 256), 256, 0, STREAM, (const T*)in, idx, nout, H, (T*)out));
   count_launch();
   return check_launch("gather_rows_bf16_kernel");
 }
@@ -908,7 +940,7 @@ extern "C" int bb_scatter_add_rows(const void* in_bf16, const int64_t* idx, int6
                                    void* stream) {
   if (nin <= 0) return 0;
   const long long n = nin * H;
-  bb::launch_pdl(scatter_add_rows_kernel, (unsigned)((n + 255) / 256), 256, 0, STREAM, (const bf16*)in_bf16, idx, nin, H, out_f32);
+  ACT_T(bb::launch_pdl(scatter_add_rows_kernel<T>, (unsigned)((n + 255) / 256), 256, 0, STREAM, (const T*)in_bf16, idx, nin, H, out_f32));
   count_launch();
   return check_launch("scatter_add_rows_kernel");
 }
@@ -916,7 +948,7 @@ extern "C" int bb_scatter_add_rows(const void* in_bf16, const int64_t* idx, int6
 extern "C" int bb_softmax_xent(const float* logits, const int64_t* labels, int64_t rows, int V, int64_t ld, float* loss,
                                const float* gscale, void* dlogits, void* stream) {
   if (rows <= 0) return 0;
-  bb::launch_pdl(softmax_xent_kernel, (unsigned)rows, 256, 0, STREAM, logits, labels, V, ld, loss, gscale, (bf16*)dlogits);
+  ACT_T(bb::launch_pdl(softmax_xent_kernel<T>, (unsigned)rows, 256, 0, STREAM, logits, labels, V, ld, loss, gscale, (T*)dlogits));
   count_launch();
   return check_launch("softmax_xent_kernel");
 }

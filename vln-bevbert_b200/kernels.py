@@ -16,9 +16,30 @@ EPI_NONE, EPI_DGELU, EPI_DRELU = 0, 1, 2
 BF16 = torch.bfloat16
 
 
+_FP32_ARM = False
+
+
 def act_dtype():
-    """dtype of activations between kernels (bf16 in the product)."""
-    return BF16
+    """dtype of activations between kernels: bf16 in the product, fp32 in the high-precision verification arm."""
+    return torch.float32 if _FP32_ARM else BF16
+
+
+def set_precision(fp32: bool) -> bool:
+    """Switches the whole library between the bf16 product path and the fp32 VERIFICATION arm (bb_set_act_f32):
+    activations, GEMM operands and every reduction in fp32 (a plain CUDA-core GEMM, the unfused attention sequence,
+    the Python sub-layer composition).  It exists so that the parity tests can hold the model to 1e-3 against the fp32
+    oracle and so separate kernel logic from bf16 rounding; it is far slower than the product path.  Returns the
+    previous setting.  Build a fresh model (weight shadows are per precision) after switching."""
+    global _FP32_ARM
+    prev = _FP32_ARM
+    _lib.load().bb_set_act_f32(1 if fp32 else 0)
+    _FP32_ARM = bool(fp32)
+    return prev
+
+
+def use_flash():
+    """fused attention core (bb_flash_*) or, in the fp32 arm, the unfused GEMM + softmax sequence"""
+    return FLASH and not _FP32_ARM
 
 
 def _p(t):
@@ -64,8 +85,8 @@ def gemm(a, b, out, M, N, K, lda, ldb, ldd, a_mn=False, b_mn=False, nb1=1, nb2=1
     """out = epi(alpha * A @ B^T) on tcgen05; a/b/out are base tensors (pointer = data_ptr()), strides in
     elements.  out dtype bf16 or f32 decides the output type.  drop = (seed, thresh, scale)."""
     lib = _lib.load()
-    _req(a, BF16, "a")
-    _req(b, BF16, "b")
+    _req(a, act_dtype(), "a")
+    _req(b, act_dtype(), "b")
     g = _lib.GemmArgs()
     g.A, g.B, g.D = a.data_ptr(), b.data_ptr(), out.data_ptr()
     g.M, g.N, g.K = M, N, K
@@ -76,10 +97,10 @@ def gemm(a, b, out, M, N, K, lda, ldb, ldd, a_mn=False, b_mn=False, nb1=1, nb2=1
     g.ldd, g.d_s1, g.d_s2 = ldd, d_s[0], d_s[1]
     if out.dtype == torch.float32:
         g.out_f32 = 1
-    elif out.dtype == BF16:
+    elif out.dtype == BF16 and not _FP32_ARM:
         g.out_f32 = 0
     else:
-        raise TypeError("gemm output must be bf16 or f32")
+        raise TypeError("gemm output must be bf16 or f32 (f32 only in the fp32 verification arm)")
     g.accumulate, g.split_k = int(accumulate), split_k
     g.alpha = alpha
     g.bias = _p(bias)
@@ -111,8 +132,9 @@ def gemm_profile_records():
 
 # ---------------------------------------------------------------------------------------------- native sub-layers
 def native_sublayers():
-    """True: blocks.py hands whole attention / FFN sub-layers to the C++ executors (csrc/layers.cu)."""
-    return True
+    """True: blocks.py hands whole attention / FFN sub-layers to the C++ executors (csrc/layers.cu); the fp32
+    verification arm runs the equivalent Python composition of the same kernels instead."""
+    return not _FP32_ARM
 
 
 def attn_desc():
@@ -160,8 +182,8 @@ def attn_scores_fwd(q, ldq, k, ldk, B, H, nq, nk, dh, ldp, kmask, bias, drop):
     a.alpha = 1.0 / (dh ** 0.5)
     a.kmask, a.bias = _p(kmask), _p(bias)
     a.seed, a.thresh, a.scale = drop
-    P = torch.empty(B, H, nq, ldp, dtype=BF16, device=q.device)
-    Pd = torch.empty(B, H, nq, ldp, dtype=BF16, device=q.device) if drop[1] else None
+    P = torch.empty(B, H, nq, ldp, dtype=act_dtype(), device=q.device)
+    Pd = torch.empty(B, H, nq, ldp, dtype=act_dtype(), device=q.device) if drop[1] else None
     a.P, a.Pd = P.data_ptr(), _p(Pd)
     _lib.check(lib.bb_attn_scores(C.byref(a), _stream()), "bb_attn_scores")
     return P, (Pd if Pd is not None else P)
@@ -176,7 +198,7 @@ def attn_scores_bwd(dctx, ldd, v, ldv, P, B, H, nq, nk, dh, ldp, drop, dbias=Non
     a.B, a.H, a.nq, a.nk, a.ldp, a.mode = B, H, nq, nk, ldp, 1
     a.alpha, a.out_scale = 1.0, 1.0 / (dh ** 0.5)
     a.seed, a.thresh, a.scale = drop
-    dS = torch.empty(B, H, nq, ldp, dtype=BF16, device=dctx.device)
+    dS = torch.empty(B, H, nq, ldp, dtype=act_dtype(), device=dctx.device)
     a.Pin, a.dS, a.dbias = P.data_ptr(), dS.data_ptr(), _p(dbias)
     _lib.check(lib.bb_attn_scores(C.byref(a), _stream()), "bb_attn_scores")
     return dS
@@ -207,8 +229,8 @@ def flash_fwd(q, k, v, B, H, nq, nk, ldq, ldk, ldv, kmask=None, bias=None, drop=
     """fused attention core (bb_flash_fwd): q/k/v are bf16 tensors whose data_ptr is element (0,0,0,0) of the
     (B, rows, H, 64) view with row stride ld*; -> (o (B,nq,H*64) bf16, lse (B,H,nq) f32)."""
     for t, n in ((q, "q"), (k, "k"), (v, "v")):
-        _req(t, BF16, n)
-    o = torch.empty(B, nq, H * 64, dtype=BF16, device=q.device)
+        _req(t, act_dtype(), n)
+    o = torch.empty(B, nq, H * 64, dtype=act_dtype(), device=q.device)
     lse = torch.empty(B, H, nq, dtype=torch.float32, device=q.device)
     a = _flash_args(q, k, v, o, lse, B, H, nq, nk, ldq, ldk, ldv, H * 64, kmask, bias, drop)
     _lib.check(_lib.load().bb_flash_fwd(C.byref(a), _stream()), "bb_flash_fwd")
@@ -222,9 +244,9 @@ def flash_bwd(q, k, v, o, lse, dout, B, H, nq, nk, ldq, ldk, ldv, kmask=None, bi
     Hd = H * 64
     a = _flash_args(q, k, v, o, lse, B, H, nq, nk, ldq, ldk, ldv, Hd, kmask, bias, drop)
     if out is None:
-        dq = torch.empty(B, nq, Hd, dtype=BF16, device=q.device)
-        dk = torch.empty(B, nk, Hd, dtype=BF16, device=q.device)
-        dv = torch.empty(B, nk, Hd, dtype=BF16, device=q.device)
+        dq = torch.empty(B, nq, Hd, dtype=act_dtype(), device=q.device)
+        dk = torch.empty(B, nk, Hd, dtype=act_dtype(), device=q.device)
+        dv = torch.empty(B, nk, Hd, dtype=act_dtype(), device=q.device)
         lddq = lddk = lddv = Hd
     else:
         dq, lddq, dk, lddk, dv, lddv = out
@@ -277,6 +299,9 @@ def bev_scatter_mean(feats, cell_idx, ncell, want_f32=True, want_bf16=True):
     fn = lib.bb_bev_scatter_mean_bf16 if feats.dtype == BF16 else lib.bb_bev_scatter_mean_f32
     B, P, Cc = feats.shape
     dev = feats.device
+    if _FP32_ARM and want_bf16:          # the "activation copy" of the pooled map is the fp32 map itself
+        o32, _, ob, cnt = bev_scatter_mean(feats, cell_idx, ncell, True, False)
+        return (o32 if want_f32 else None), o32.clone(), ob, cnt
     o32 = torch.empty(B, ncell, Cc, dtype=torch.float32, device=dev) if want_f32 else None
     o16 = torch.empty(B, ncell, Cc, dtype=BF16, device=dev) if want_bf16 else None
     ob = torch.empty(B, ncell, dtype=torch.uint8, device=dev)
@@ -304,7 +329,7 @@ def cast_to_act(src, drop=(0, 0, 1.0), out=None):
     _req(src, torch.float32, "src")
     src = src.contiguous()
     if out is None:
-        out = torch.empty(src.shape, dtype=BF16, device=src.device)
+        out = torch.empty(src.shape, dtype=act_dtype(), device=src.device)
     _lib.check(lib.bb_cast_f32_bf16(src.data_ptr(), out.data_ptr(), src.numel(), drop[0], drop[1], drop[2],
                                     _stream()), "bb_cast_f32_bf16")
     return out
@@ -312,7 +337,7 @@ def cast_to_act(src, drop=(0, 0, 1.0), out=None):
 
 def cast_to_f32(src):
     lib = _lib.load()
-    _req(src, BF16, "src")
+    _req(src, act_dtype(), "src")
     src = src.contiguous()
     out = torch.empty(src.shape, dtype=torch.float32, device=src.device)
     _lib.check(lib.bb_cast_bf16_f32(src.data_ptr(), out.data_ptr(), src.numel(), _stream()), "bb_cast_bf16_f32")
@@ -321,7 +346,7 @@ def cast_to_f32(src):
 
 def dropout_act(src, drop, out=None):
     lib = _lib.load()
-    _req(src, BF16, "src")
+    _req(src, act_dtype(), "src")
     if out is None:
         out = torch.empty_like(src)
     _lib.check(lib.bb_dropout_bf16(src.data_ptr(), out.data_ptr(), src.numel(), drop[0], drop[1], drop[2], _stream()),
@@ -334,7 +359,7 @@ def layernorm_fwd(x, residual, gamma, beta, eps, drop_in=(0, 0, 1.0), drop_out=(
     lib = _lib.load()
     rows, H = x.shape
     dev = x.device
-    y = torch.empty(rows, H, dtype=BF16, device=dev)
+    y = torch.empty(rows, H, dtype=act_dtype(), device=dev)
     y32 = torch.empty(rows, H, dtype=torch.float32, device=dev) if want_f32 else None
     mean = torch.empty(rows, dtype=torch.float32, device=dev)
     rstd = torch.empty(rows, dtype=torch.float32, device=dev)
@@ -351,8 +376,9 @@ def layernorm_bwd(dy, x, residual, gamma, mean, rstd, drop_in=(0, 0, 1.0), drop_
     lib = _lib.load()
     rows, H = x.shape
     dev = x.device
-    dx = torch.empty(rows, H, dtype=torch.float32 if dx_f32 else BF16, device=dev) if want_dx else None
-    dres = torch.empty(rows, H, dtype=BF16, device=dev) if want_dres else None
+    dx_f32 = dx_f32 or _FP32_ARM
+    dx = torch.empty(rows, H, dtype=torch.float32 if dx_f32 else act_dtype(), device=dev) if want_dx else None
+    dres = torch.empty(rows, H, dtype=act_dtype(), device=dev) if want_dres else None
     _lib.check(lib.bb_layernorm_bwd(dy.data_ptr(), int(dy.dtype == torch.float32), x.data_ptr(),
                                     int(x.dtype == torch.float32), _p(residual), gamma.data_ptr(), mean.data_ptr(),
                                     rstd.data_ptr(), rows, H, drop_in[0], drop_in[1], drop_in[2], drop_out[0],
@@ -364,7 +390,7 @@ def layernorm_bwd(dy, x, residual, gamma, mean, rstd, drop_in=(0, 0, 1.0), drop_
 def colsum(x, N, out=None):
     """column sums of a bf16 (rows, N) row-major matrix -> f32 [N] (accumulated into `out` if given)."""
     lib = _lib.load()
-    _req(x, BF16, "x")
+    _req(x, act_dtype(), "x")
     rows = x.numel() // N
     if out is None:
         out = torch.zeros(N, dtype=torch.float32, device=x.device)
@@ -375,8 +401,8 @@ def colsum(x, N, out=None):
 def softmax_fwd(scores, kmask, bias, nbatch, H, nq, nk, ld, drop=(0, 0, 1.0)):
     lib = _lib.load()
     dev = scores.device
-    probs = torch.empty(nbatch, H, nq, ld, dtype=BF16, device=dev)
-    pd = torch.empty(nbatch, H, nq, ld, dtype=BF16, device=dev) if drop[1] else None
+    probs = torch.empty(nbatch, H, nq, ld, dtype=act_dtype(), device=dev)
+    pd = torch.empty(nbatch, H, nq, ld, dtype=act_dtype(), device=dev) if drop[1] else None
     _lib.check(lib.bb_softmax_fwd(scores.data_ptr(), _p(kmask), _p(bias), nbatch, H, nq, nk, ld, drop[0], drop[1],
                                   drop[2], probs.data_ptr(), _p(pd), _stream()), "bb_softmax_fwd")
     return probs, (pd if pd is not None else probs)
@@ -384,7 +410,7 @@ def softmax_fwd(scores, kmask, bias, nbatch, H, nq, nk, ld, drop=(0, 0, 1.0)):
 
 def softmax_bwd(probs, dprobs, nbatch, H, nq, nk, ld, drop, out_scale, dbias=None):
     lib = _lib.load()
-    ds = torch.empty(nbatch, H, nq, ld, dtype=BF16, device=probs.device)
+    ds = torch.empty(nbatch, H, nq, ld, dtype=act_dtype(), device=probs.device)
     _lib.check(lib.bb_softmax_bwd(probs.data_ptr(), dprobs.data_ptr(), nbatch, H, nq, nk, ld, drop[0], drop[1],
                                   drop[2], out_scale, ds.data_ptr(), _p(dbias), _stream()), "bb_softmax_bwd")
     return ds
@@ -410,7 +436,7 @@ def embed_scatter_grad(ids, dz, L, padding_idx, dword, dpos, dtype0):
 def gather_rows(src, idx, H):
     """out[r] = src[idx[r]] (bf16 rows of width H); idx int64, negative -> zero row."""
     lib = _lib.load()
-    out = torch.empty(idx.numel(), H, dtype=BF16, device=src.device)
+    out = torch.empty(idx.numel(), H, dtype=act_dtype(), device=src.device)
     _lib.check(lib.bb_gather_rows_bf16(src.data_ptr(), idx.data_ptr(), idx.numel(), H, out.data_ptr(), _stream()),
                "bb_gather_rows_bf16")
     return out
@@ -446,7 +472,7 @@ def add_rows(a, b=None, table=None, idx=None, vec=None):
     """a (+ b) (+ table[idx]) (+ vec) over bf16 (rows,H)."""
     lib = _lib.load()
     rows, H = a.shape
-    out = torch.empty(rows, H, dtype=BF16, device=a.device)
+    out = torch.empty(rows, H, dtype=act_dtype(), device=a.device)
     _lib.check(lib.bb_add_rows(a.data_ptr(), _p(b), _p(table), _p(idx), _p(vec), rows, H, out.data_ptr(), _stream()),
                "bb_add_rows")
     return out
@@ -460,7 +486,7 @@ def scale_rows_(x, g, rows, ld):
 
 def segment_wsum(src, seg_off, idx, w, nseg, H):
     lib = _lib.load()
-    out = torch.empty(nseg, H, dtype=BF16, device=src.device)
+    out = torch.empty(nseg, H, dtype=act_dtype(), device=src.device)
     _lib.check(lib.bb_segment_wsum(src.data_ptr(), seg_off.data_ptr(), idx.data_ptr(), w.data_ptr(), nseg, H,
                                    out.data_ptr(), _stream()), "bb_segment_wsum")
     return out
@@ -492,7 +518,7 @@ def softmax_xent(logits, labels, V, ld, want_grad=True):
     lib = _lib.load()
     rows = logits.shape[0]
     loss = torch.empty(rows, dtype=torch.float32, device=logits.device)
-    dl = torch.empty(rows, ld, dtype=BF16, device=logits.device) if want_grad else None
+    dl = torch.empty(rows, ld, dtype=act_dtype(), device=logits.device) if want_grad else None
     _lib.check(lib.bb_softmax_xent(logits.data_ptr(), labels.data_ptr(), rows, V, ld, loss.data_ptr(), 0, _p(dl),
                                    _stream()), "bb_softmax_xent")
     return loss, dl
