@@ -385,6 +385,279 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
 }
 
 
+// ================================================================================================ forward, streaming
+// Second-generation forward (the default): K / V stream through shared memory in 64-key blocks, S is double-buffered in
+// TMEM (2 x 64 columns + 64 for O = 256 allocated columns) and the CTA is small (6 warps, 96 KB of shared memory), so
+// TWO CTAs share an SM and each one overlaps its own tensor-pipe work with its element-wise work: profiling of the
+// first version (whole key range in TMEM, one CTA per SM) showed 28 % issue utilisation -- the warps mostly waited on
+// mbarriers (loads, MMAs) with nothing else resident to run.
+//   pass A: for every key block  S = Q K^T -> running row maximum                     (tensor pipe + 1 FMNMX / element)
+//   pass B: for every key block  S = Q K^T again -> P = 2^(S - max) -> O += P V       (K is re-streamed from L2)
+// A thread owns a complete query row (TMEM lane), so max and sum need no exchange between warps; recomputing S costs
+// tensor time that is idle anyway (a 128 x 64 x 64 product is 128 cycles) and removes the online-softmax rescaling of O.
+constexpr int F2_NT = 192;                 // warp 0 TMA, warp 1 MMA, warps 2..5 softmax / epilogue
+constexpr int F2_O = 0, F2_S = 64;         // TMEM columns: O [0,64), S buffers [64,128) and [128,192)
+constexpr int F2_KST = 3;                  // K / V ring depth
+
+__device__ __forceinline__ void named_sync_128() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+__global__ void __launch_bounds__(F2_NT, 2)
+attn_tc_fwd2_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk,
+                    const __grid_constant__ CUtensorMap tv, const FwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + Q_BYTES;
+  uint8_t* sV = sK + F2_KST * BLK_BYTES;
+  uint8_t* sP = sV + F2_KST * BLK_BYTES;
+  const int nblk = (p.nk + KB - 1) / KB;
+  float* skm = reinterpret_cast<float*>(sP + 2 * P_BYTES);        // [nblk * 64] log2-domain key mask
+  float* skf = skm + nblk * KB;                                   // [nblk * 2] per 32-key chunk: mask not all zero
+  uint64_t* bars = reinterpret_cast<uint64_t*>(skf + ((nblk * 2 + 3) & ~3));
+  uint64_t* q_full = bars + 0;
+  uint64_t* o_full = bars + 1;
+  uint64_t* k_full = bars + 2;     // [3]
+  uint64_t* k_free = bars + 5;     // [3]
+  uint64_t* v_full = bars + 8;     // [3]
+  uint64_t* v_free = bars + 11;    // [3]
+  uint64_t* s_full = bars + 14;    // [2]
+  uint64_t* s_free = bars + 16;    // [2]
+  uint64_t* p_full = bars + 18;    // [2]
+  uint64_t* p_free = bars + 20;    // [2]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 22);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * BM, h = blockIdx.y, b = blockIdx.z;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tq);
+      tma_prefetch_desc(&tk);
+      tma_prefetch_desc(&tv);
+      mbar_init(q_full, 1);
+      mbar_init(o_full, 1);
+      for (int i = 0; i < F2_KST; ++i) {
+        mbar_init(&k_full[i], 1);
+        mbar_init(&k_free[i], 1);
+        mbar_init(&v_full[i], 1);
+        mbar_init(&v_free[i], 1);
+      }
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&s_full[i], 1);
+        mbar_init(&s_free[i], 128);
+        mbar_init(&p_full[i], 128);
+        mbar_init(&p_free[i], 1);
+      }
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_ptr_smem, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();
+  pdl_trigger();
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer: Q, K (pass A), K + V (pass B)
+    if (lane == 0) {
+      mbar_expect_tx(q_full, Q_BYTES);
+      tma_load_4d(sQ, &tq, q_full, 0, q0, h, b);
+      for (int i = 0; i < 2 * nblk; ++i) {
+        const int j = i < nblk ? i : i - nblk;
+        const int st = i % F2_KST;
+        mbar_wait(&k_free[st], ((i / F2_KST) & 1) ^ 1);
+        mbar_expect_tx(&k_full[st], BLK_BYTES);
+        tma_load_4d(sK + st * BLK_BYTES, &tk, &k_full[st], 0, j * KB, h, b);
+        if (i >= nblk) {
+          const int vs = j % F2_KST;
+          mbar_wait(&v_free[vs], ((j / F2_KST) & 1) ^ 1);
+          mbar_expect_tx(&v_full[vs], BLK_BYTES);
+          tma_load_4d(sV + vs * BLK_BYTES, &tv, &v_full[vs], 0, j * KB, h, b);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc_s = umma_idesc_bf16(BM, KB, 0, 0), idesc_pv = umma_idesc_bf16(BM, 64, 0, 1);
+      const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV), aP = smem_u32(sP);
+      mbar_wait(q_full, 0);
+      auto issue_pv = [&](int j) {
+        const int slot = j & 1, vs = j % F2_KST;
+        mbar_wait(&p_full[slot], (j >> 1) & 1);
+        mbar_wait(&v_full[vs], (j / F2_KST) & 1);
+        tc_fence_after();
+        const int ksteps = (min(KB, p.nk - j * KB) + 15) >> 4;
+        for (int k = 0; k < ksteps; ++k)
+          umma_bf16_ss(tmem_base + F2_O, umma_smem_desc(aP + slot * P_BYTES + k * 32, 16, 1024),
+                       umma_smem_desc(aV + vs * BLK_BYTES + k * 2048, 8192, 1024), idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
+        umma_commit(&p_free[slot]);
+        umma_commit(&v_free[vs]);
+      };
+      for (int i = 0; i < 2 * nblk; ++i) {
+        const int st = i % F2_KST, sb = i & 1;
+        mbar_wait(&k_full[st], (i / F2_KST) & 1);
+        mbar_wait(&s_free[sb], ((i >> 1) & 1) ^ 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16_ss(tmem_base + F2_S + sb * KB, umma_smem_desc(aQ + k * 32, 16, 1024),
+                       umma_smem_desc(aK + st * BLK_BYTES + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
+        umma_commit(&s_full[sb]);
+        umma_commit(&k_free[st]);
+        if (i > nblk) issue_pv(i - nblk - 1);     // one block of look-ahead: S(j+1) is computed while P(j) is produced
+      }
+      issue_pv(nblk - 1);
+      umma_commit(o_full);
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ softmax + epilogue: thread = query row
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const int st_ = threadIdx.x - 64;            // 0..127
+    const uint32_t trow = tmem_base + (uint32_t(quarter * 32) << 16);
+    const int64_t grow = ((int64_t)b * p.H + h) * p.nq + q0 + row;
+    const uint32_t rh = p.thresh ? rng_u32(p.seed, (uint64_t)grow) : 0u;
+    const uint32_t t16s = p.thresh & 0xFFFF0000u;
+    const uint32_t a_skm = smem_u32(skm), a_skf = smem_u32(skf);
+    const uint32_t prow0 = smem_u32(sP) + (row >> 3) * 1024 + (row & 7) * 128;
+    const int sw = row & 7;
+    for (int i = st_; i < nblk * KB; i += 128) {      // a warp covers exactly one 32-key chunk per iteration
+      const float kv = i < p.nk ? (p.kmask ? __ldg(p.kmask + (int64_t)b * p.nk + i) * LOG2E : 0.f) : -INFINITY;
+      sts_f(a_skm + i * 4, kv);
+      const bool any = __any_sync(0xffffffffu, kv != 0.f);
+      if (lane == 0) sts_f(a_skf + (i >> 5) * 4, any ? 1.f : 0.f);
+    }
+    named_sync_128();
+    // ---- pass A: row maximum
+    float mx = -INFINITY, mraw = -INFINITY;
+    for (int i = 0; i < nblk; ++i) {
+      const int sb = i & 1;
+      mbar_wait(&s_full[sb], (i >> 1) & 1);
+      tc_fence_after();
+      uint32_t r0[32], r1[32];
+      tmem_ld32(trow + F2_S + sb * KB, r0);
+      tmem_ld32(trow + F2_S + sb * KB + 32, r1);
+      tmem_ld_wait32(r0);
+      tmem_ld_wait32(r1);
+      tc_fence_before();
+      mbar_arrive(&s_free[sb]);
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const uint32_t(&r)[32] = c ? r1 : r0;
+        if (lds_f(a_skf + (i * 2 + c) * 4) == 0.f) {
+#pragma unroll
+          for (int e = 0; e < 32; e += 2) mraw = fmaxf(mraw, fmaxf(__uint_as_float(r[e]), __uint_as_float(r[e + 1])));
+        } else {
+          const uint32_t km4 = a_skm + (i * KB + c * 32) * 4;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float4 km = lds_f4(km4 + e * 16);
+            mx = fmaxf(mx, fmaf(__uint_as_float(r[4 * e + 0]), p.a2, km.x));
+            mx = fmaxf(mx, fmaf(__uint_as_float(r[4 * e + 1]), p.a2, km.y));
+            mx = fmaxf(mx, fmaf(__uint_as_float(r[4 * e + 2]), p.a2, km.z));
+            mx = fmaxf(mx, fmaf(__uint_as_float(r[4 * e + 3]), p.a2, km.w));
+          }
+        }
+      }
+    }
+    const float m = fmaxf(mx, mraw * p.a2);      // a2 > 0
+    const float ms = m == -INFINITY ? 0.f : m;
+    // ---- pass B: probabilities -> P blocks (A operand of the PV product)
+    float lsum = 0.f;
+    for (int j = 0; j < nblk; ++j) {
+      const int i = nblk + j, sb = i & 1, slot = j & 1;
+      mbar_wait(&s_full[sb], (i >> 1) & 1);
+      tc_fence_after();
+      uint32_t r0[32], r1[32];
+      tmem_ld32(trow + F2_S + sb * KB, r0);
+      tmem_ld32(trow + F2_S + sb * KB + 32, r1);
+      tmem_ld_wait32(r0);
+      tmem_ld_wait32(r1);
+      tc_fence_before();
+      mbar_arrive(&s_free[sb]);                   // the next S block is computed while this one is exponentiated
+      mbar_wait(&p_free[slot], ((j >> 1) & 1) ^ 1);
+      const uint32_t prow = prow0 + slot * P_BYTES;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const uint32_t(&r)[32] = c ? r1 : r0;
+        const bool masked = lds_f(a_skf + (j * 2 + c) * 4) != 0.f;
+        const uint32_t km4 = a_skm + (j * KB + c * 32) * 4;
+        const uint32_t pair0 = (uint32_t)(j * KB + c * 32) >> 1;
+#pragma unroll
+        for (int e = 0; e < 8; e += 2) {
+          uint32_t w[4];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int x = e + u;
+            float e0, e1, e2, e3;
+            if (masked) {
+              const float4 km = lds_f4(km4 + x * 16);
+              e0 = ex2f(fmaf(__uint_as_float(r[4 * x + 0]), p.a2, km.x - ms));
+              e1 = ex2f(fmaf(__uint_as_float(r[4 * x + 1]), p.a2, km.y - ms));
+              e2 = ex2f(fmaf(__uint_as_float(r[4 * x + 2]), p.a2, km.z - ms));
+              e3 = ex2f(fmaf(__uint_as_float(r[4 * x + 3]), p.a2, km.w - ms));
+            } else {
+              e0 = ex2f(fmaf(__uint_as_float(r[4 * x + 0]), p.a2, -ms));
+              e1 = ex2f(fmaf(__uint_as_float(r[4 * x + 1]), p.a2, -ms));
+              e2 = ex2f(fmaf(__uint_as_float(r[4 * x + 2]), p.a2, -ms));
+              e3 = ex2f(fmaf(__uint_as_float(r[4 * x + 3]), p.a2, -ms));
+            }
+            lsum += (e0 + e1) + (e2 + e3);
+            if (p.thresh) {     // kept probabilities are not rescaled here: 1/(1-p) is folded into the O epilogue
+              const uint32_t x0 = mix_pair(rh, pair0 + 2 * x), x1 = mix_pair(rh, pair0 + 2 * x + 1);
+              e0 = (x0 << 16) >= t16s ? e0 : 0.f;
+              e1 = x0 >= t16s ? e1 : 0.f;
+              e2 = (x1 << 16) >= t16s ? e2 : 0.f;
+              e3 = x1 >= t16s ? e3 : 0.f;
+            }
+            w[2 * u] = pack2(e0, e1);
+            w[2 * u + 1] = pack2(e2, e3);
+          }
+          sts_u4(prow + (((c * 4 + (e >> 1)) ^ sw) << 4), w[0], w[1], w[2], w[3]);
+        }
+      }
+      fence_proxy_async();
+      mbar_arrive(&p_full[slot]);
+    }
+    // ---- epilogue: O row -> bf16, log2-domain log-sum-exp
+    mbar_wait(o_full, 0);
+    tc_fence_after();
+    const float inv = lsum > 0.f ? (p.thresh ? p.scale : 1.0f) / lsum : 0.f;
+    bf16* dst = p.out + (int64_t)b * p.o_bs + (int64_t)(q0 + row) * p.ldo + h * 64;
+    const bool valid = q0 + row < p.nq;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t r[32];
+      tmem_ld32(trow + F2_O + c * 32, r);
+      tmem_ld_wait32(r);
+      if (valid) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          reinterpret_cast<uint4*>(dst + c * 32)[i] =
+              make_uint4(pack2(__uint_as_float(r[8 * i]) * inv, __uint_as_float(r[8 * i + 1]) * inv),
+                         pack2(__uint_as_float(r[8 * i + 2]) * inv, __uint_as_float(r[8 * i + 3]) * inv),
+                         pack2(__uint_as_float(r[8 * i + 4]) * inv, __uint_as_float(r[8 * i + 5]) * inv),
+                         pack2(__uint_as_float(r[8 * i + 6]) * inv, __uint_as_float(r[8 * i + 7]) * inv));
+      }
+    }
+    if (valid && p.lse) p.lse[grow] = lsum > 0.f ? m + log2f(lsum) : INFINITY;
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
 // ================================================================================================ backward
 // Two passes over the (query tile x key tile) grid of a (sample, head), both with 128 x 128 score tiles in TMEM and the
 // thread <-> query-row mapping of the forward kernel:
@@ -751,6 +1024,7 @@ static int init_once() {
   if (cudaGetDevice(&dev) != cudaSuccess) return set_error("cudaGetDevice failed");
   cudaDeviceGetAttribute(&g_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
   if (cudaFuncSetAttribute(attn_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin) != cudaSuccess ||
+      cudaFuncSetAttribute(attn_tc_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin) != cudaSuccess ||
       cudaFuncSetAttribute(attn_tc_bwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin) != cudaSuccess ||
       cudaFuncSetAttribute(attn_tc_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem_optin) != cudaSuccess)
     return set_error("cudaFuncSetAttribute failed for the attn_tc kernels");
@@ -785,10 +1059,36 @@ bool fwd_supported(const bb_flash_args* a) {
   return true;
 }
 
+static int fwd_version() {      // BB_ATTN_FWD=1 selects the first-generation kernel (whole key range in TMEM)
+  static const int v = [] {
+    const char* e = getenv("BB_ATTN_FWD");
+    return e ? atoi(e) : 2;
+  }();
+  return v;
+}
+
 int launch_fwd(const bb_flash_args* a, void* stream) {
   if (int e = init_once()) return e;
   FwdParams p;
   memset(&p, 0, sizeof(p));
+  if (fwd_version() == 2 && a->nk <= 4096) {
+    p.out = (bf16*)a->o; p.o_bs = a->o_bs; p.ldo = a->ldo; p.lse = a->lse; p.kmask = a->kmask;
+    p.B = a->B; p.H = a->H; p.nq = a->nq; p.nk = a->nk;
+    p.a2 = a->alpha * LOG2E;
+    p.seed = a->seed; p.thresh = a->thresh; p.scale = a->scale;
+    p.trace = nullptr;
+    CUtensorMap tq, tk, tv;
+    if (int e = make_tmap_bf16_4d(&tq, a->q, 64, a->nq, a->H, a->B, a->ldq, 64, a->q_bs, BM)) return e;
+    if (int e = make_tmap_bf16_4d(&tk, a->k, 64, a->nk, a->H, a->B, a->ldk, 64, a->k_bs, KB)) return e;
+    if (int e = make_tmap_bf16_4d(&tv, a->v, 64, a->nk, a->H, a->B, a->ldv, 64, a->v_bs, KB)) return e;
+    const int nblk = (a->nk + KB - 1) / KB;
+    const size_t smem = 1024 + Q_BYTES + 2 * (size_t)F2_KST * BLK_BYTES + 2 * P_BYTES + (size_t)nblk * KB * 4 +
+                        (size_t)((nblk * 2 + 3) & ~3) * 4 + 24 * 8 + 64;
+    const dim3 grid((unsigned)((a->nq + BM - 1) / BM), (unsigned)a->H, (unsigned)a->B);
+    launch_pdl(attn_tc_fwd2_kernel, grid, dim3(F2_NT), smem, (cudaStream_t)stream, tq, tk, tv, p);
+    count_launch();
+    return check_launch("attn_tc_fwd2_kernel");
+  }
   p.out = (bf16*)a->o; p.o_bs = a->o_bs; p.ldo = a->ldo; p.lse = a->lse; p.kmask = a->kmask;
   p.B = a->B; p.H = a->H; p.nq = a->nq; p.nk = a->nk;
   p.nsb = (a->nk + MAX_SBK - 1) / MAX_SBK;
