@@ -1,0 +1,6 @@
+#!/bin/bash
+mkdir -p gpurun_out
+export PYTHONDONTWRITEBYTECODE=1
+timeout 900 python -m pytest tests/test_kernels_gpu.py -m gpu -q -rf --no-header -p no:cacheprovider -k "tcgen05 or flash" > gpurun_out/r2j_test_attn.log 2>&1
+echo "== attn tests rc=$?"; tail -n 6 gpurun_out/r2j_test_attn.log
+timeout 300 python scripts/bench_attn.py > gpurun_out/r2j_bench_attn.log 2>&1; cat gpurun_out/r2j_bench_attn.log

@@ -33,12 +33,21 @@ def _oracle_grads(sd, b, task, cfg, autocast=False):
     return out.detach().float(), {n: v.grad.clone() for n, v in sd.items() if v.grad is not None}
 
 
-def _compare(task, cfg, scfg, seed=7, loss_tol=1e-2, global_grad_tol=1e-2, grad_tol=5e-2):
-    """Losses: relative L2 <= 1e-2 (north_star bf16 tolerance).  Gradients: relative L2 over all parameters
-    <= 1e-2 where the problem is well conditioned (MLM); for the softmax-CE action/object heads, whose gradient
-    terms cancel across near-identical tokens at random init, even PyTorch's own bf16 autocast of the reference
-    loses 5-8 %% -- there we require to stay within 2.5x of that autocast error (measured on B200: 1.0-2.0x),
-    globally and per parameter (3x)."""
+# bf16 product path, fixed bars (the kernel / host LOGIC is held to 1e-3 by test_fp32_verification_arm_holds_1e3; what
+# is left here is the precision class of bf16 storage between kernels).  Conditioning of the gradient differs by task:
+# the softmax-CE action / object heads (sap, og) at random init amplify rounding ~10x more than the token-level
+# losses -- scripts/precision_study.py reproduces the GPU numbers on CPU with bf16 storage emulated at the same sites
+# (9.7e-2 for full-depth SAP) and shows PyTorch's own bf16 autocast of the reference at 6-7e-2 on the same inputs.
+GLOBAL_GRAD_BAR = {"mlm": 3e-2, "masksem": 4e-2, "sem": 4e-2, "mrc": 4e-2, "sap": 1.3e-1, "og": 1.3e-1}
+
+
+def _compare(task, cfg, scfg, seed=7, loss_tol=1e-2, global_grad_tol=None, grad_tol=None):
+    """Losses: relative L2 <= 1e-2 (north_star bf16 tolerance).  Gradients: global relative L2 over all parameters
+    <= the fixed per-task bar above AND <= 2.5x the error of PyTorch's bf16 autocast of the reference on the same
+    inputs (so a regression of our precision relative to the standard mixed-precision recipe is caught even inside the
+    bar); per parameter <= 2x the global bar or 3x autocast."""
+    global_grad_tol = GLOBAL_GRAD_BAR[task] if global_grad_tol is None else global_grad_tol
+    grad_tol = 2.0 * global_grad_tol if grad_tol is None else grad_tol
     model = synth.det_init_(GlocalTextPathCMTPreTraining(cfg), seed=3).to(DEV).train()
     sd = {k: v.detach().float().cpu().clone().requires_grad_(True) for k, v in model.state_dict().items()}
     b = synth.make_batch(scfg, seed=seed, task=task)
@@ -58,7 +67,7 @@ def _compare(task, cfg, scfg, seed=7, loss_tol=1e-2, global_grad_tol=1e-2, grad_
     for n, e in worst:
         print("    %-75s ours %.3e autocast %.3e |g_ref| %.3e" % (n, e, errs_ac[n], float(rg[n].norm())))
     assert le < loss_tol, le
-    assert glob < max(global_grad_tol, 2.5 * glob_ac), (glob, glob_ac)
+    assert glob < global_grad_tol and glob < max(1e-2, 2.5 * glob_ac), (glob, global_grad_tol, glob_ac)
     bad = {n: (e, errs_ac[n]) for n, e in errs.items() if e > max(grad_tol, 3.0 * errs_ac[n])}
     assert not bad, bad
     return le, glob

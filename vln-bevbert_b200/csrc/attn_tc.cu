@@ -395,7 +395,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
 //   pass B: for every key block  S = Q K^T again -> P = 2^(S - max) -> O += P V       (K is re-streamed from L2)
 // A thread owns a complete query row (TMEM lane), so max and sum need no exchange between warps; recomputing S costs
 // tensor time that is idle anyway (a 128 x 64 x 64 product is 128 cycles) and removes the online-softmax rescaling of O.
-constexpr int F2_NT = 192;                 // warp 0 TMA, warp 1 MMA, warps 2..5 softmax / epilogue
+constexpr int F2_NT = 320;                 // warp 0 TMA, warp 1 MMA, warps 2..9 softmax / epilogue (row x key half)
 constexpr int F2_O = 0, F2_S = 64;         // TMEM columns: O [0,64), S buffers [64,128) and [128,192)
 constexpr int F2_KST = 3;                  // K / V ring depth
 
@@ -411,9 +411,12 @@ attn_tc_fwd2_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
   uint8_t* sV = sK + F2_KST * BLK_BYTES;
   uint8_t* sP = sV + F2_KST * BLK_BYTES;
   const int nblk = (p.nk + KB - 1) / KB;
+  const bool keep_s = nblk <= 2;     // both S blocks fit the two TMEM buffers: pass B re-reads them instead of recomputing
+  const int n_s = keep_s ? nblk : 2 * nblk;
   float* skm = reinterpret_cast<float*>(sP + 2 * P_BYTES);        // [nblk * 64] log2-domain key mask
   float* skf = skm + nblk * KB;                                   // [nblk * 2] per 32-key chunk: mask not all zero
-  uint64_t* bars = reinterpret_cast<uint64_t*>(skf + ((nblk * 2 + 3) & ~3));
+  float* sx = skf + ((nblk * 2 + 3) & ~3);                        // [2][128] row max / row sum exchange between halves
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sx + 2 * BM);
   uint64_t* q_full = bars + 0;
   uint64_t* o_full = bars + 1;
   uint64_t* k_full = bars + 2;     // [3]
@@ -444,8 +447,8 @@ attn_tc_fwd2_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
       }
       for (int i = 0; i < 2; ++i) {
         mbar_init(&s_full[i], 1);
-        mbar_init(&s_free[i], 128);
-        mbar_init(&p_full[i], 128);
+        mbar_init(&s_free[i], 256);
+        mbar_init(&p_full[i], 256);
         mbar_init(&p_free[i], 1);
       }
       fence_mbar_init();
@@ -466,15 +469,15 @@ attn_tc_fwd2_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
     if (lane == 0) {
       mbar_expect_tx(q_full, Q_BYTES);
       tma_load_4d(sQ, &tq, q_full, 0, q0, h, b);
-      for (int i = 0; i < 2 * nblk; ++i) {
+      for (int i = 0; i < n_s; ++i) {
         const int j = i < nblk ? i : i - nblk;
         const int st = i % F2_KST;
-        mbar_wait(&k_free[st], ((i / F2_KST) & 1) ^ 1);
+        mbar_wait_relaxed(&k_free[st], ((i / F2_KST) & 1) ^ 1);
         mbar_expect_tx(&k_full[st], BLK_BYTES);
         tma_load_4d(sK + st * BLK_BYTES, &tk, &k_full[st], 0, j * KB, h, b);
-        if (i >= nblk) {
+        if (keep_s || i >= nblk) {
           const int vs = j % F2_KST;
-          mbar_wait(&v_free[vs], ((j / F2_KST) & 1) ^ 1);
+          mbar_wait_relaxed(&v_free[vs], ((j / F2_KST) & 1) ^ 1);
           mbar_expect_tx(&v_full[vs], BLK_BYTES);
           tma_load_4d(sV + vs * BLK_BYTES, &tv, &v_full[vs], 0, j * KB, h, b);
         }
@@ -486,11 +489,11 @@ attn_tc_fwd2_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
     if (lane == 0) {
       const uint32_t idesc_s = umma_idesc_bf16(BM, KB, 0, 0), idesc_pv = umma_idesc_bf16(BM, 64, 0, 1);
       const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV), aP = smem_u32(sP);
-      mbar_wait(q_full, 0);
+      mbar_wait_relaxed(q_full, 0);
       auto issue_pv = [&](int j) {
         const int slot = j & 1, vs = j % F2_KST;
-        mbar_wait(&p_full[slot], (j >> 1) & 1);
-        mbar_wait(&v_full[vs], (j / F2_KST) & 1);
+        mbar_wait_relaxed(&p_full[slot], (j >> 1) & 1);
+        mbar_wait_relaxed(&v_full[vs], (j / F2_KST) & 1);
         tc_fence_after();
         const int ksteps = (min(KB, p.nk - j * KB) + 15) >> 4;
         for (int k = 0; k < ksteps; ++k)
@@ -499,10 +502,10 @@ attn_tc_fwd2_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
         umma_commit(&p_free[slot]);
         umma_commit(&v_free[vs]);
       };
-      for (int i = 0; i < 2 * nblk; ++i) {
+      for (int i = 0; i < n_s; ++i) {
         const int st = i % F2_KST, sb = i & 1;
-        mbar_wait(&k_full[st], (i / F2_KST) & 1);
-        mbar_wait(&s_free[sb], ((i >> 1) & 1) ^ 1);
+        mbar_wait_relaxed(&k_full[st], (i / F2_KST) & 1);
+        if (!keep_s) mbar_wait_relaxed(&s_free[sb], ((i >> 1) & 1) ^ 1);
         tc_fence_after();
 #pragma unroll
         for (int k = 0; k < 4; ++k)
@@ -510,144 +513,147 @@ attn_tc_fwd2_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constan
                        umma_smem_desc(aK + st * BLK_BYTES + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
         umma_commit(&s_full[sb]);
         umma_commit(&k_free[st]);
-        if (i > nblk) issue_pv(i - nblk - 1);     // one block of look-ahead: S(j+1) is computed while P(j) is produced
+        if (!keep_s && i > nblk) issue_pv(i - nblk - 1);   // one block of look-ahead: S(j+1) runs while P(j) is produced
+      }
+      if (keep_s) {
+        for (int j = 0; j + 1 < nblk; ++j) issue_pv(j);
       }
       issue_pv(nblk - 1);
       umma_commit(o_full);
     }
     __syncwarp();
   } else {
-    // ------------------------------------------------------------------ softmax + epilogue: thread = query row
+    // ------------------------------------------------------------------ softmax + epilogue: thread = (query row, key half)
     const int quarter = warp & 3;
+    const int hf = (warp - 2) >> 2;              // columns [32 hf, 32 hf + 32) of every 64-key block
     const int row = quarter * 32 + lane;
-    const int st_ = threadIdx.x - 64;            // 0..127
+    const int st_ = threadIdx.x - 64;            // 0..255
     const uint32_t trow = tmem_base + (uint32_t(quarter * 32) << 16);
     const int64_t grow = ((int64_t)b * p.H + h) * p.nq + q0 + row;
     const uint32_t rh = p.thresh ? rng_u32(p.seed, (uint64_t)grow) : 0u;
     const uint32_t t16s = p.thresh & 0xFFFF0000u;
-    const uint32_t a_skm = smem_u32(skm), a_skf = smem_u32(skf);
+    const uint32_t a_skm = smem_u32(skm), a_skf = smem_u32(skf), a_sx = smem_u32(sx);
     const uint32_t prow0 = smem_u32(sP) + (row >> 3) * 1024 + (row & 7) * 128;
     const int sw = row & 7;
-    for (int i = st_; i < nblk * KB; i += 128) {      // a warp covers exactly one 32-key chunk per iteration
+    for (int i = st_; i < nblk * KB; i += 256) {      // a warp covers exactly one 32-key chunk per iteration
       const float kv = i < p.nk ? (p.kmask ? __ldg(p.kmask + (int64_t)b * p.nk + i) * LOG2E : 0.f) : -INFINITY;
       sts_f(a_skm + i * 4, kv);
       const bool any = __any_sync(0xffffffffu, kv != 0.f);
       if (lane == 0) sts_f(a_skf + (i >> 5) * 4, any ? 1.f : 0.f);
     }
-    named_sync_128();
-    // ---- pass A: row maximum
+    named_sync_256();
+    // ---- pass A: row maximum over this thread's half of every block
     float mx = -INFINITY, mraw = -INFINITY;
     for (int i = 0; i < nblk; ++i) {
       const int sb = i & 1;
       mbar_wait(&s_full[sb], (i >> 1) & 1);
       tc_fence_after();
-      uint32_t r0[32], r1[32];
-      tmem_ld32(trow + F2_S + sb * KB, r0);
-      tmem_ld32(trow + F2_S + sb * KB + 32, r1);
-      tmem_ld_wait32(r0);
-      tmem_ld_wait32(r1);
-      tc_fence_before();
-      mbar_arrive(&s_free[sb]);
+      uint32_t r[32];
+      tmem_ld32(trow + F2_S + sb * KB + hf * 32, r);
+      tmem_ld_wait32(r);
+      if (!keep_s) {
+        tc_fence_before();
+        mbar_arrive(&s_free[sb]);
+      }
+      if (lds_f(a_skf + (i * 2 + hf) * 4) == 0.f) {
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        const uint32_t(&r)[32] = c ? r1 : r0;
-        if (lds_f(a_skf + (i * 2 + c) * 4) == 0.f) {
+        for (int e = 0; e < 32; e += 2) mraw = fmaxf(mraw, fmaxf(__uint_as_float(r[e]), __uint_as_float(r[e + 1])));
+      } else {
+        const uint32_t km4 = a_skm + (i * KB + hf * 32) * 4;
 #pragma unroll
-          for (int e = 0; e < 32; e += 2) mraw = fmaxf(mraw, fmaxf(__uint_as_float(r[e]), __uint_as_float(r[e + 1])));
-        } else {
-          const uint32_t km4 = a_skm + (i * KB + c * 32) * 4;
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const float4 km = lds_f4(km4 + e * 16);
-            mx = fmaxf(mx, fmaf(__uint_as_float(r[4 * e + 0]), p.a2, km.x));
-            mx = fmaxf(mx, fmaf(__uint_as_float(r[4 * e + 1]), p.a2, km.y));
-            mx = fmaxf(mx, fmaf(__uint_as_float(r[4 * e + 2]), p.a2, km.z));
-            mx = fmaxf(mx, fmaf(__uint_as_float(r[4 * e + 3]), p.a2, km.w));
-          }
+        for (int e = 0; e < 8; ++e) {
+          const float4 km = lds_f4(km4 + e * 16);
+          mx = fmaxf(mx, fmaf(__uint_as_float(r[4 * e + 0]), p.a2, km.x));
+          mx = fmaxf(mx, fmaf(__uint_as_float(r[4 * e + 1]), p.a2, km.y));
+          mx = fmaxf(mx, fmaf(__uint_as_float(r[4 * e + 2]), p.a2, km.z));
+          mx = fmaxf(mx, fmaf(__uint_as_float(r[4 * e + 3]), p.a2, km.w));
         }
       }
     }
-    const float m = fmaxf(mx, mraw * p.a2);      // a2 > 0
+    sts_f(a_sx + (hf * BM + row) * 4, fmaxf(mx, mraw * p.a2));      // a2 > 0
+    named_sync_256();
+    const float m = fmaxf(lds_f(a_sx + row * 4), lds_f(a_sx + (BM + row) * 4));
     const float ms = m == -INFINITY ? 0.f : m;
+    named_sync_256();                                                // sx is reused for the row sums below
     // ---- pass B: probabilities -> P blocks (A operand of the PV product)
     float lsum = 0.f;
     for (int j = 0; j < nblk; ++j) {
-      const int i = nblk + j, sb = i & 1, slot = j & 1;
-      mbar_wait(&s_full[sb], (i >> 1) & 1);
-      tc_fence_after();
-      uint32_t r0[32], r1[32];
-      tmem_ld32(trow + F2_S + sb * KB, r0);
-      tmem_ld32(trow + F2_S + sb * KB + 32, r1);
-      tmem_ld_wait32(r0);
-      tmem_ld_wait32(r1);
-      tc_fence_before();
-      mbar_arrive(&s_free[sb]);                   // the next S block is computed while this one is exponentiated
+      const int i = keep_s ? j : nblk + j, sb = i & 1, slot = j & 1;
+      if (!keep_s) {
+        mbar_wait(&s_full[sb], (i >> 1) & 1);
+        tc_fence_after();
+      }
+      uint32_t r[32];
+      tmem_ld32(trow + F2_S + sb * KB + hf * 32, r);
+      tmem_ld_wait32(r);
+      if (!keep_s) {
+        tc_fence_before();
+        mbar_arrive(&s_free[sb]);                 // the next S block is computed while this one is exponentiated
+      }
       mbar_wait(&p_free[slot], ((j >> 1) & 1) ^ 1);
       const uint32_t prow = prow0 + slot * P_BYTES;
+      const bool masked = lds_f(a_skf + (j * 2 + hf) * 4) != 0.f;
+      const uint32_t km4 = a_skm + (j * KB + hf * 32) * 4;
+      const uint32_t pair0 = (uint32_t)(j * KB + hf * 32) >> 1;
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        const uint32_t(&r)[32] = c ? r1 : r0;
-        const bool masked = lds_f(a_skf + (j * 2 + c) * 4) != 0.f;
-        const uint32_t km4 = a_skm + (j * KB + c * 32) * 4;
-        const uint32_t pair0 = (uint32_t)(j * KB + c * 32) >> 1;
+      for (int e = 0; e < 8; e += 2) {
+        uint32_t w[4];
 #pragma unroll
-        for (int e = 0; e < 8; e += 2) {
-          uint32_t w[4];
-#pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const int x = e + u;
-            float e0, e1, e2, e3;
-            if (masked) {
-              const float4 km = lds_f4(km4 + x * 16);
-              e0 = ex2f(fmaf(__uint_as_float(r[4 * x + 0]), p.a2, km.x - ms));
-              e1 = ex2f(fmaf(__uint_as_float(r[4 * x + 1]), p.a2, km.y - ms));
-              e2 = ex2f(fmaf(__uint_as_float(r[4 * x + 2]), p.a2, km.z - ms));
-              e3 = ex2f(fmaf(__uint_as_float(r[4 * x + 3]), p.a2, km.w - ms));
-            } else {
-              e0 = ex2f(fmaf(__uint_as_float(r[4 * x + 0]), p.a2, -ms));
-              e1 = ex2f(fmaf(__uint_as_float(r[4 * x + 1]), p.a2, -ms));
-              e2 = ex2f(fmaf(__uint_as_float(r[4 * x + 2]), p.a2, -ms));
-              e3 = ex2f(fmaf(__uint_as_float(r[4 * x + 3]), p.a2, -ms));
-            }
-            lsum += (e0 + e1) + (e2 + e3);
-            if (p.thresh) {     // kept probabilities are not rescaled here: 1/(1-p) is folded into the O epilogue
-              const uint32_t x0 = mix_pair(rh, pair0 + 2 * x), x1 = mix_pair(rh, pair0 + 2 * x + 1);
-              e0 = (x0 << 16) >= t16s ? e0 : 0.f;
-              e1 = x0 >= t16s ? e1 : 0.f;
-              e2 = (x1 << 16) >= t16s ? e2 : 0.f;
-              e3 = x1 >= t16s ? e3 : 0.f;
-            }
-            w[2 * u] = pack2(e0, e1);
-            w[2 * u + 1] = pack2(e2, e3);
+        for (int u = 0; u < 2; ++u) {
+          const int x = e + u;
+          float e0, e1, e2, e3;
+          if (masked) {
+            const float4 km = lds_f4(km4 + x * 16);
+            e0 = ex2f(fmaf(__uint_as_float(r[4 * x + 0]), p.a2, km.x - ms));
+            e1 = ex2f(fmaf(__uint_as_float(r[4 * x + 1]), p.a2, km.y - ms));
+            e2 = ex2f(fmaf(__uint_as_float(r[4 * x + 2]), p.a2, km.z - ms));
+            e3 = ex2f(fmaf(__uint_as_float(r[4 * x + 3]), p.a2, km.w - ms));
+          } else {
+            e0 = ex2f(fmaf(__uint_as_float(r[4 * x + 0]), p.a2, -ms));
+            e1 = ex2f(fmaf(__uint_as_float(r[4 * x + 1]), p.a2, -ms));
+            e2 = ex2f(fmaf(__uint_as_float(r[4 * x + 2]), p.a2, -ms));
+            e3 = ex2f(fmaf(__uint_as_float(r[4 * x + 3]), p.a2, -ms));
           }
-          sts_u4(prow + (((c * 4 + (e >> 1)) ^ sw) << 4), w[0], w[1], w[2], w[3]);
+          lsum += (e0 + e1) + (e2 + e3);
+          if (p.thresh) {     // kept probabilities are not rescaled here: 1/(1-p) is folded into the O epilogue
+            const uint32_t x0 = mix_pair(rh, pair0 + 2 * x), x1 = mix_pair(rh, pair0 + 2 * x + 1);
+            e0 = (x0 << 16) >= t16s ? e0 : 0.f;
+            e1 = x0 >= t16s ? e1 : 0.f;
+            e2 = (x1 << 16) >= t16s ? e2 : 0.f;
+            e3 = x1 >= t16s ? e3 : 0.f;
+          }
+          w[2 * u] = pack2(e0, e1);
+          w[2 * u + 1] = pack2(e2, e3);
         }
+        sts_u4(prow + (((hf * 4 + (e >> 1)) ^ sw) << 4), w[0], w[1], w[2], w[3]);
       }
       fence_proxy_async();
       mbar_arrive(&p_full[slot]);
     }
-    // ---- epilogue: O row -> bf16, log2-domain log-sum-exp
+    sts_f(a_sx + (hf * BM + row) * 4, lsum);
+    named_sync_256();
+    const float l = lds_f(a_sx + row * 4) + lds_f(a_sx + (BM + row) * 4);
+    // ---- epilogue: this thread's 32 columns of the O row -> bf16, log2-domain log-sum-exp
     mbar_wait(o_full, 0);
     tc_fence_after();
-    const float inv = lsum > 0.f ? (p.thresh ? p.scale : 1.0f) / lsum : 0.f;
-    bf16* dst = p.out + (int64_t)b * p.o_bs + (int64_t)(q0 + row) * p.ldo + h * 64;
+    const float inv = l > 0.f ? (p.thresh ? p.scale : 1.0f) / l : 0.f;
     const bool valid = q0 + row < p.nq;
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
+    {
       uint32_t r[32];
-      tmem_ld32(trow + F2_O + c * 32, r);
+      tmem_ld32(trow + F2_O + hf * 32, r);
       tmem_ld_wait32(r);
       if (valid) {
+        bf16* dst = p.out + (int64_t)b * p.o_bs + (int64_t)(q0 + row) * p.ldo + h * 64 + hf * 32;
 #pragma unroll
         for (int i = 0; i < 4; ++i)
-          reinterpret_cast<uint4*>(dst + c * 32)[i] =
+          reinterpret_cast<uint4*>(dst)[i] =
               make_uint4(pack2(__uint_as_float(r[8 * i]) * inv, __uint_as_float(r[8 * i + 1]) * inv),
                          pack2(__uint_as_float(r[8 * i + 2]) * inv, __uint_as_float(r[8 * i + 3]) * inv),
                          pack2(__uint_as_float(r[8 * i + 4]) * inv, __uint_as_float(r[8 * i + 5]) * inv),
                          pack2(__uint_as_float(r[8 * i + 6]) * inv, __uint_as_float(r[8 * i + 7]) * inv));
       }
     }
-    if (valid && p.lse) p.lse[grow] = lsum > 0.f ? m + log2f(lsum) : INFINITY;
+    if (valid && hf == 0 && p.lse) p.lse[grow] = l > 0.f ? m + log2f(l) : INFINITY;
   }
 
   tc_fence_before();
@@ -1083,7 +1089,7 @@ int launch_fwd(const bb_flash_args* a, void* stream) {
     if (int e = make_tmap_bf16_4d(&tv, a->v, 64, a->nk, a->H, a->B, a->ldv, 64, a->v_bs, KB)) return e;
     const int nblk = (a->nk + KB - 1) / KB;
     const size_t smem = 1024 + Q_BYTES + 2 * (size_t)F2_KST * BLK_BYTES + 2 * P_BYTES + (size_t)nblk * KB * 4 +
-                        (size_t)((nblk * 2 + 3) & ~3) * 4 + 24 * 8 + 64;
+                        (size_t)((nblk * 2 + 3) & ~3) * 4 + 2 * BM * 4 + 24 * 8 + 64;
     const dim3 grid((unsigned)((a->nq + BM - 1) / BM), (unsigned)a->H, (unsigned)a->B);
     launch_pdl(attn_tc_fwd2_kernel, grid, dim3(F2_NT), smem, (cudaStream_t)stream, tq, tk, tv, p);
     count_launch();
