@@ -100,10 +100,38 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+WORKLOAD = "r2r"
+WORKLOADS = {
+    # BASELINE.json configs[1] (the headline): scripts/pt_r2r.bash:4 --task_ratio mlm.5.sap.5.masksem.1
+    "r2r": dict(mix=["mlm", "sap"] * 5 + ["masksem"], model={}, synth={},
+                name="R2R pre-train step, BASELINE configs[1]: batch 32/GPU, 80-token instruction, 36 views x 768, 21x21 BEV, "
+                     "<=20 topo nodes"),
+    # configs[3]: XLM-R vocabulary / positions (configs/rxr_model.json:20,30), 512-token instructions, same task mix
+    # (scripts/pt_rxr.bash:4)
+    "rxr": dict(mix=["mlm", "sap"] * 5 + ["masksem"], model=dict(vocab_size=250002, max_position_embeddings=514),
+                synth=dict(txt_len=512, vocab_lo=1000, vocab_hi=250000, n_mask_tokens=77),
+                name="RxR pre-train step, BASELINE configs[3]: XLM-R vocab 250002, 512-token instruction, 36 views x 768, "
+                     "21x21 BEV, <=20 topo nodes"),
+    # configs[4]: object tokens (configs/rvr_model.json obj_feat_size 768, rvr_pretrain.json max_objects 20),
+    # scripts/pt_rvr.bash:4 --task_ratio mlm.1.mrc.1.sap.1.og.1
+    "reverie": dict(mix=["mlm", "mrc", "sap", "og"], model=dict(obj_feat_size=768, obj_prob_size=1000,
+                                                                 pretrain_tasks=["mlm", "mrc", "sap", "og"]),
+                    synth=dict(obj_feat_size=768, obj_max=20, obj_prob_size=1000),
+                    name="REVERIE pre-train step, BASELINE configs[4]: 36 pano views + <=20 object tokens x 768, object "
+                         "grounding / region classification heads, 21x21 BEV"),
+}
+
+
 def full_config():
     from bevbert_b200.config import make_config
-    # reference R2R model config with the north_star's 768-d view features; dropout as set_dropout(model, 0.1) leaves it
-    return make_config(hidden_dropout_prob=0.1, attention_probs_dropout_prob=0.1, feat_dropout=0.1)
+    # reference model config with the north_star's 768-d view features; dropout as set_dropout(model, 0.1) leaves it
+    return make_config(hidden_dropout_prob=0.1, attention_probs_dropout_prob=0.1, feat_dropout=0.1,
+                       **WORKLOADS[WORKLOAD]["model"])
+
+
+def synth_config(batch_size):
+    from bevbert_b200 import synth
+    return synth.SynthConfig(batch_size=batch_size, **WORKLOADS[WORKLOAD]["synth"])
 
 
 # ====================================================================================== reference arm (CPU oracle)
@@ -123,7 +151,7 @@ def run_reference(args, rank):
     del model
     ocfg = R.OracleConfig(cfg, drop_p=0.1, feat_drop_p=0.1)
     Bs = args.ref_batch
-    scfg = synth.SynthConfig(batch_size=Bs)
+    scfg = synth_config(Bs)
     batches = {t: synth.make_batch(scfg, seed=1234, task=t) for t in set(MIX)}
 
     def step(i):
@@ -208,7 +236,7 @@ def run_ours(args, rank, world, local_rank):
         opt = AdamW(build_param_groups(model, 0.01), lr=5e-5, betas=(0.9, 0.98), eps=1e-6, max_grad_norm=5.0,
                     runtime=model.rt)
     Bs = args.batch
-    scfg = synth.SynthConfig(batch_size=Bs)
+    scfg = synth_config(Bs)
     from bevbert_b200.model.ops import prepare_batch
     # prepare_batch = collate-time host index building (DataLoader-worker work in the reference's pipeline)
     host = {t: [prepare_batch(pin_batch(synth.make_batch(scfg, seed=1234 + 97 * rank + 13 * j, task=t))) for j in range(2)]
@@ -219,7 +247,7 @@ def run_ours(args, rank, world, local_rank):
     wire = torch.bfloat16 if args.wire == "bf16" else None
     host_e2e = host if wire is None else {t: [prepare_batch(b, wire_dtype=wire) for b in bs] for t, bs in host.items()}
 
-    def train_step(batch, task):
+    def eager_step(batch, task):
         loss = net(batch, task).mean()
         loss.backward()
         if reduce_grads is not None:
@@ -227,6 +255,13 @@ def run_ours(args, rank, world, local_rank):
         opt.step()
         opt.zero_grad(set_to_none=True)
         return loss
+
+    graphed = None
+    if args.graphs and not args.ddp and not args.torch_optim:
+        # whole-step CUDA-graph replay (bevbert_b200/graphs.py): one graph per (task, static batch buffers)
+        from bevbert_b200.graphs import GraphedTrainStep
+        graphed = GraphedTrainStep(net, opt, reduce_grads)
+    train_step = graphed if graphed is not None else eager_step
 
     def sync_all():
         torch.cuda.synchronize()
@@ -243,9 +278,11 @@ def run_ours(args, rank, world, local_rank):
 
     # Setup, untimed: one step per resident (task, batch) pair so that every tensor shape of the cycle has been seen by
     # the caching allocator and the per-task gradient arenas are sized before the W warm-up steps start
+    setup_reps = 4 if graphed is not None else 1      # graph mode: two eager steps, the capture and a first replay
     for t in sorted(set(MIX)):
         for j in range(2):
-            train_step(resident[t][j], t)
+            for _ in range(setup_reps):
+                train_step(resident[t][j], t)
     torch.cuda.synchronize()
 
     # ------------------------------------------------------------------ device-resident throughput ("value")
@@ -258,13 +295,19 @@ def run_ours(args, rank, world, local_rank):
     K.reset_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync_all()
+    host_t0 = time.perf_counter()
     e0.record()
     for i in range(args.steps):
         train_step(resident[MIX[i % len(MIX)]][i % 2], MIX[i % len(MIX)])
     e1.record()
+    host_enqueue_ms = (time.perf_counter() - host_t0) * 1e3 / args.steps     # host time to enqueue a step
     sync_all()
     ms = e0.elapsed_time(e1)
-    launches = K.launch_count()
+    launches = K.launch_count()          # kernels launched eagerly (host-counted) ...
+    if graphed is not None:              # ... plus the kernels inside every replayed graph
+        for i in range(args.steps):
+            n = graphed.launches(resident[MIX[i % len(MIX)]][i % 2], MIX[i % len(MIX)])
+            launches += n or 0
     clk = clocks.stop() if rank == 0 else None
     if world > 1:
         t = torch.tensor([ms], device=dev)
@@ -293,6 +336,15 @@ def run_ours(args, rank, world, local_rank):
         return dev_in[(t, j)], t, ev, (t, j)
     h2d = sum(tensor_bytes(host_e2e[MIX[i % len(MIX)]][i % 2]) for i in range(args.steps)) / args.steps
     loss_host = torch.zeros(args.steps, dtype=torch.float32).pin_memory()
+    if graphed is not None:                          # untimed: capture the graphs of the static e2e input buffers
+        for t in sorted(set(MIX)):
+            for j in range(2):
+                for k, v in host_e2e[t][j].items():
+                    if torch.is_tensor(v):
+                        dev_in[(t, j)][k].copy_(v, non_blocking=True)
+                for _ in range(setup_reps):
+                    train_step(dev_in[(t, j)], t)
+        sync_all()
     for i in range(min(args.warmup, 3)):            # untimed: first use of the wire-format kernels / copy stream
         b, t, ev, key = fetch(i)
         torch.cuda.current_stream().wait_event(ev)
@@ -375,7 +427,7 @@ def run_ours(args, rank, world, local_rank):
         sd = {k: v.detach().float().cpu().clone().requires_grad_(True) for k, v in model.state_dict().items()}
         ocfg = R.OracleConfig(cfg, drop_p=0.1, feat_drop_p=0.1)
         cb = args.ref_batch
-        cbatches = {t: synth.make_batch(synth.SynthConfig(batch_size=cb), seed=1234, task=t) for t in set(MIX)}
+        cbatches = {t: synth.make_batch(synth_config(cb), seed=1234, task=t) for t in set(MIX)}
         per_task = {}
         for t in ("mlm", "sap", "masksem"):
             ts = []
@@ -397,15 +449,18 @@ def run_ours(args, rank, world, local_rank):
             "metric": "pretrain_samples_per_s", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "R2R pre-train step, BASELINE configs[1]: batch %d/GPU, 80-token instruction, 36 views x 768, "
-                                   "21x21 BEV, <=20 topo nodes; lift-splat + fwd + bwd%s + fused AdamW; tasks cycle "
-                                   "mlm,sap x5 + masksem; dropout 0.1" % (Bs, " + DDP NCCL grad all-reduce" if world > 1 else ""),
+            "config": {"workload": "%s; batch %d/GPU; lift-splat + fwd + bwd%s + grad-norm clip + AdamW (reference update "
+                                   "rule); tasks cycle %s; dropout 0.1" % (
+                                       WORKLOADS[WORKLOAD]["name"], Bs, " + NCCL grad all-reduce" if world > 1 else "",
+                                       ",".join(MIX)),
                        "global_batch": Bs * world, "parallelism": "dp%d" % world,
                        "l2": "per-step inputs (%.0f MB) and saved activations exceed the 126 MB L2" % (h2d / 1e6)},
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
                     "wire": "bf16 grid/view features, other inputs as collated" if wire is not None else "fp32 as collated",
                     "ms_per_step": ms_e2e / args.steps, "last_loss": losses[-1] if losses else None},
-            "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
+            "gpu_launches": int(launches), "host_enqueue_ms_per_step": round(host_enqueue_ms, 3),
+            "step_mode": "cuda-graph replay per (task, static batch); sem/masksem eager" if graphed is not None else "eager launches",
+            "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
         }
         print(json.dumps(out))
     if world > 1:
@@ -421,12 +476,20 @@ def main():
     ap.add_argument("--batch", type=int, default=32, help="samples per GPU per step")
     ap.add_argument("--ref-batch", type=int, default=2, help="batch of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--config", default="r2r", choices=sorted(WORKLOADS), help="workload: r2r = BASELINE configs[1] "
+                    "(headline), rxr = configs[3], reverie = configs[4]")
+    ap.add_argument("--graphs", type=int, default=1, help="1: replay each (task, batch) step as one CUDA graph (default); 0: eager launches")
     ap.add_argument("--torch-optim", action="store_true", help="torch.optim.AdamW(fused=True) instead of bevbert_b200.optim.AdamW")
     ap.add_argument("--wire", choices=("bf16", "fp32"), default="bf16",
                     help="host dtype of the large feature tensors in the end-to-end leg")
     ap.add_argument("--ddp", action="store_true", help="wrap with torch DDP instead of the flat gradient all-reduce")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    global WORKLOAD, MIX
+    WORKLOAD = args.config
+    MIX = list(WORKLOADS[WORKLOAD]["mix"])
+    if WORKLOAD == "reverie":
+        args.graphs = 0      # the object-token path sizes its tensors from device data (host sync): not capturable
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

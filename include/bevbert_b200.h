@@ -25,6 +25,12 @@ int bb_abi_version(void);
 int64_t bb_launch_count(void);
 void bb_reset_launch_count(void);
 
+/* Registers a 64-bit word in DEVICE memory that every kernel XORs into its dropout seed (NULL = none, the default).
+ * Needed for CUDA-graph replay of a training step: seeds are kernel parameters and therefore frozen in a captured graph;
+ * the caller rewrites this word before each replay to draw fresh masks (forward and backward of one step see the same
+ * value, so masks are still replayed exactly).  Synchronous (cudaMemcpyToSymbol); call it once, outside capture. */
+int bb_set_drop_salt_ptr(const uint64_t* device_word);
+
 /* ---------------------------------------------------------------------------------------------
  * Batched bf16 GEMM on tcgen05 tensor cores, TMA-fed, fp32 accumulation in TMEM.
  *   D[b] = epi( alpha * A[b] (M x K) * B[b]^T (N x K) )
@@ -72,9 +78,13 @@ int bb_gemm_bf16(const bb_gemm_args* args, void* stream);
  * Returns the previous mode. */
 int bb_set_act_f32(int on);
 int bb_get_act_f32(void);
-/* Optional measurement hook (bench.py roofline): while enabled, every bb_gemm_bf16 launch is bracketed by a pair
- * of CUDA events on its stream.  bb_gemm_profile(1) resets and starts, (0) stops; _count() = launches recorded;
- * _read(i, &ms, dims) synchronises on launch i and returns its duration and (M, N, K, batches, a_mn, b_mn). */
+/* Optional measurement hook (bench.py roofline): the caller registers a device buffer of 2 x capacity 64-bit words
+ * (starts initialised to ~0, ends to 0); while profiling is enabled every bb_gemm_bf16 launch gets the next slot and its
+ * CTAs stamp %globaltimer into it (min of the starts, max of the ends): the kernel's own execution span, with no events
+ * between launches (programmatic dependent launch and CUDA-graph capture stay intact; a graph replay re-stamps the slots
+ * of the launches it contains).  bb_gemm_profile(1) resets the slot counter and starts, (0) stops; _count() = launches
+ * recorded; _read(i, &ms, dims) copies slot i back (synchronous) and returns its span and (M, N, K, batches, a_mn, b_mn). */
+int bb_gemm_profile_buffer(unsigned long long* device_buf, int64_t capacity_launches);
 /* Debug: when device_buf is not NULL every bb_gemm_bf16 launch writes, per CTA c and local tile i < 16, four
  * %globaltimer stamps at device_buf[(c*16+i)*4 + {0: MMA issue start, 1: MMA issue end, 2: epilogue start, 3: end}]. */
 int bb_gemm_trace(long long* device_buf);

@@ -96,9 +96,11 @@ _SIGNATURES = {
     "bb_launch_count": (c_i64, []),
     "bb_reset_launch_count": (None, []),
     "bb_gemm_bf16": (c_int, [C.POINTER(GemmArgs), c_void_p]),
+    "bb_set_drop_salt_ptr": (c_int, [c_void_p]),
     "bb_set_act_f32": (c_int, [c_int]),
     "bb_get_act_f32": (c_int, []),
     "bb_gemm_trace": (c_int, [c_void_p]),
+    "bb_gemm_profile_buffer": (c_int, [c_void_p, c_i64]),
     "bb_gemm_profile": (c_int, [c_int]),
     "bb_gemm_profile_count": (c_i64, []),
     "bb_gemm_profile_read": (c_int, [c_i64, C.POINTER(c_float), C.POINTER(c_i64)]),

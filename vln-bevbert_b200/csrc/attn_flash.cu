@@ -624,3 +624,5 @@ extern "C" int bb_flash_bwd(const bb_flash_args* a, void* stream) {
   count_launch(2);
   return check_launch("flash_bwd kernels");
 }
+
+namespace bb { int set_salt_attn_flash(const unsigned long long* p) { return set_drop_salt_ptr_tu(p) == cudaSuccess ? 0 : -1; } }

@@ -385,3 +385,5 @@ extern "C" int bb_attn_scores(const bb_attn_scores_args* a, void* stream_) {
   count_launch();
   return check_launch("attn_scores_kernel");
 }
+
+namespace bb { int set_salt_attn_scores(const unsigned long long* p) { return set_drop_salt_ptr_tu(p) == cudaSuccess ? 0 : -1; } }

@@ -1163,3 +1163,5 @@ extern "C" int bb_attn_tc_trace(long long* device_buf) {
   bb::fat::g_trace = device_buf;
   return 0;
 }
+
+namespace bb { int set_salt_attn_tc(const unsigned long long* p) { return set_drop_salt_ptr_tu(p) == cudaSuccess ? 0 : -1; } }

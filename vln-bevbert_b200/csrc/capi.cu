@@ -37,3 +37,18 @@ extern "C" const char* bb_last_error(void) { return bb::g_err; }
 extern "C" int bb_abi_version(void) { return 1; }
 extern "C" int64_t bb_launch_count(void) { return bb::g_launches.load(); }
 extern "C" void bb_reset_launch_count(void) { bb::g_launches.store(0); }
+
+namespace bb {
+int set_salt_gemm_tc(const unsigned long long*);
+int set_salt_rowops(const unsigned long long*);
+int set_salt_attn_flash(const unsigned long long*);
+int set_salt_attn_tc(const unsigned long long*);
+int set_salt_attn_scores(const unsigned long long*);
+int set_salt_gemm_f32(const unsigned long long*);
+}  // namespace bb
+extern "C" int bb_set_drop_salt_ptr(const uint64_t* device_word) {
+  const unsigned long long* p = reinterpret_cast<const unsigned long long*>(device_word);
+  int rc = bb::set_salt_gemm_tc(p) | bb::set_salt_rowops(p) | bb::set_salt_attn_flash(p) | bb::set_salt_attn_tc(p) |
+           bb::set_salt_attn_scores(p) | bb::set_salt_gemm_f32(p);
+  return rc ? bb::set_error("bb_set_drop_salt_ptr: cudaMemcpyToSymbol failed") : 0;
+}

@@ -134,3 +134,5 @@ extern "C" int bb_set_act_f32(int on) {
   return prev;
 }
 extern "C" int bb_get_act_f32(void) { return bb::g_act_f32; }
+
+namespace bb { int set_salt_gemm_f32(const unsigned long long* p) { return set_drop_salt_ptr_tu(p) == cudaSuccess ? 0 : -1; } }

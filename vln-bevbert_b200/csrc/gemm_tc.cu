@@ -59,6 +59,7 @@ struct GemmKParams {
   int staged;         // coalesced epilogue stores through the smem staging area (BB_GEMM_STAGED=0 turns it off)
   int fast_gelu;      // experiment: Abramowitz-Stegun erf on approximate MUFU ops instead of erff()
   long long* trace;   // debug: per CTA and local tile 4 globaltimer stamps (mma start/end, epilogue start/end) or null
+  unsigned long long* prof;   // measurement: [0] = min over CTAs of the start stamp, [1] = max of the end stamp, or null
 };
 
 __device__ __forceinline__ long long gtimer() {
@@ -151,6 +152,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   // from here on global memory is read and written.
   pdl_wait();
   pdl_trigger();
+  if (p.prof && threadIdx.x == 0) atomicMin(p.prof, (unsigned long long)gtimer());
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -581,6 +583,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   tc_fence_before();
   if (CTAS == 2) cluster_sync_all();   // the leader's MMAs read the peer's smem and write its TMEM until the very end
   else __syncthreads();
+  if (p.prof && threadIdx.x == 0) atomicMax(p.prof + 1, (unsigned long long)gtimer());
   if (warp == 2) {
     tc_fence_after();
     if (CTAS == 2) tmem_dealloc_2sm(tmem_base, TMEM_COLS);
@@ -672,14 +675,18 @@ static inline int make_map(CUtensorMap* map, const void* base, uint64_t inner, u
   return bb::make_tmap_bf16_4d(map, base, inner, rows, nb1, nb2, ld, s1, s2, box_rows);
 }
 
-// ---- optional per-launch timing (bench.py roofline): CUDA events around every gemm_tc_kernel launch
+// ---- optional per-launch timing (bench.py roofline): every launch gets a slot of two 64-bit words in a caller-provided
+// device buffer; CTAs stamp %globaltimer into it (min of the starts after griddepcontrol.wait, max of the ends), so the
+// measured span is the kernel's own execution -- no events between launches, programmatic dependent launch and CUDA-graph
+// replay stay intact (a replay overwrites the slots of its launches).
 struct ProfRec {
-  cudaEvent_t e0, e1;
   long long dims[6];  // M, N, K, batches, a_mn, b_mn
 };
 static bool g_prof_on = false;
 static std::vector<ProfRec> g_prof;
 static size_t g_prof_used = 0;
+static unsigned long long* g_prof_buf = nullptr;
+static size_t g_prof_cap = 0;
 
 static long long* g_trace = nullptr;   // bb_gemm_trace(): device buffer of (grid x 16 x 4) timestamps, debug only
 static int g_num_sms = 0;
@@ -888,18 +895,13 @@ extern "C" int bb_gemm_bf16(const bb_gemm_args* a, void* stream_) {
   if (total > 0x7fffffffLL) return set_error("bb_gemm_bf16: too many tiles");
   const int units = ctas == 2 ? max_pairs() : g_num_sms;
   const int grid = (total < units ? (int)total : units) * ctas;
-  ProfRec* rec = nullptr;
-  if (g_prof_on) {
-    if (g_prof_used == g_prof.size()) {
-      ProfRec r;
-      cudaEventCreate(&r.e0);
-      cudaEventCreate(&r.e1);
-      g_prof.push_back(r);
-    }
-    rec = &g_prof[g_prof_used++];
+  if (g_prof_on && g_prof_buf && g_prof_used < g_prof_cap) {
+    if (g_prof_used == g_prof.size()) g_prof.push_back(ProfRec());
+    ProfRec* rec = &g_prof[g_prof_used];
     rec->dims[0] = a->M; rec->dims[1] = a->N; rec->dims[2] = a->K; rec->dims[3] = (long long)nb1 * nb2;
     rec->dims[4] = p.a_mn; rec->dims[5] = p.b_mn;
-    cudaEventRecord(rec->e0, stream);
+    p.prof = g_prof_buf + 2 * g_prof_used;
+    ++g_prof_used;
   }
   auto go = [&](auto k1, auto k2) {
     if (ctas == 2) bb::launch_pdl_cluster(k2, grid, NUM_THREADS, smem_bytes, stream, 2, ta, tb, p, (int)total);
@@ -908,7 +910,6 @@ extern "C" int bb_gemm_bf16(const bb_gemm_args* a, void* stream_) {
   if (epi == 1) go(gemm_tc_kernel<1, 1>, gemm_tc_kernel<2, 1>);
   else if (epi == 2) go(gemm_tc_kernel<1, 2>, gemm_tc_kernel<2, 2>);
   else go(gemm_tc_kernel<1, 0>, gemm_tc_kernel<2, 0>);
-  if (rec) cudaEventRecord(rec->e1, stream);
   count_launch();
   return check_launch("gemm_tc_kernel");
 }
@@ -918,7 +919,13 @@ extern "C" int bb_gemm_trace(long long* device_buf) {
   return 0;
 }
 
+extern "C" int bb_gemm_profile_buffer(unsigned long long* device_buf, int64_t capacity_launches) {
+  bb::g_prof_buf = device_buf;
+  bb::g_prof_cap = device_buf ? (size_t)capacity_launches : 0;
+  return 0;
+}
 extern "C" int bb_gemm_profile(int enable) {
+  if (enable && !bb::g_prof_buf) return bb::set_error("bb_gemm_profile: register a device buffer with bb_gemm_profile_buffer first");
   bb::g_prof_on = enable != 0;
   if (enable) bb::g_prof_used = 0;
   return 0;
@@ -927,9 +934,12 @@ extern "C" int64_t bb_gemm_profile_count(void) { return (int64_t)bb::g_prof_used
 extern "C" int bb_gemm_profile_read(int64_t idx, float* ms, int64_t* dims6) {
   using namespace bb;
   if (idx < 0 || (size_t)idx >= g_prof_used) return set_error("bb_gemm_profile_read: index out of range");
-  ProfRec& r = g_prof[idx];
-  if (cudaEventSynchronize(r.e1) != cudaSuccess) return set_error("bb_gemm_profile_read: event sync failed");
-  if (cudaEventElapsedTime(ms, r.e0, r.e1) != cudaSuccess) return set_error("bb_gemm_profile_read: elapsed time failed");
-  for (int i = 0; i < 6; ++i) dims6[i] = r.dims[i];
+  unsigned long long t[2];
+  if (cudaMemcpy(t, g_prof_buf + 2 * idx, sizeof(t), cudaMemcpyDeviceToHost) != cudaSuccess)
+    return set_error("bb_gemm_profile_read: cudaMemcpy failed");
+  *ms = (t[1] > t[0] && t[0] != ~0ull) ? (float)((double)(t[1] - t[0]) * 1e-6) : 0.f;
+  for (int i = 0; i < 6; ++i) dims6[i] = g_prof[idx].dims[i];
   return 0;
 }
+
+namespace bb { int set_salt_gemm_tc(const unsigned long long* p) { return set_drop_salt_ptr_tu(p) == cudaSuccess ? 0 : -1; } }

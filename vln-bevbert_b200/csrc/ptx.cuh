@@ -291,7 +291,19 @@ __device__ __forceinline__ float dgelu_fast(float x) {
 // Counter-based RNG for dropout: 32 random bits from (seed, 64-bit element index) with a 32-bit avalanche hash
 // (two multiply-xorshift rounds); stateless, so backward regenerates the identical mask.  Kept cheap on purpose:
 // the fused attention epilogue evaluates it once per probability with only a few warps per SM.
+// Device-resident salt, XORed into every dropout seed: a CUDA graph bakes the per-site seeds into its kernel nodes, so
+// the per-step variation of the masks comes from one 64-bit word in device memory that the caller rewrites before each
+// replay (bb_set_drop_salt_ptr registers its address; NULL = no salt).  One copy of the pointer per translation unit.
+static __constant__ const unsigned long long* g_drop_salt_ptr = nullptr;
+static inline cudaError_t set_drop_salt_ptr_tu(const unsigned long long* p) {
+  return cudaMemcpyToSymbol(g_drop_salt_ptr, &p, sizeof(p));
+}
+__device__ __forceinline__ uint64_t drop_salt() {
+  const unsigned long long* p = g_drop_salt_ptr;
+  return p ? __ldg(p) : 0ull;
+}
 __device__ __forceinline__ uint32_t rng_u32(uint64_t seed, uint64_t idx) {
+  seed ^= drop_salt();
   uint32_t x = static_cast<uint32_t>(idx) ^ (static_cast<uint32_t>(idx >> 32) * 0x9E3779B1u) ^
                static_cast<uint32_t>(seed) ^ (static_cast<uint32_t>(seed >> 32) * 0x85EBCA6Bu);
   x ^= x >> 16;

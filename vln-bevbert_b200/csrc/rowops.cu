@@ -335,8 +335,10 @@ layernorm_fwd_kernel(const XT* __restrict__ x, const T* __restrict__ res, const 
 
 // Backward. Grid-stride over rows (one warp per row); each lane keeps per-column dgamma/dbeta partials,
 // reduced through shared memory and flushed with one atomicAdd per column per block.
-template <typename DYT, typename XT, typename DXT, typename T>
-__global__ void __launch_bounds__(LN_WARPS * 32)
+// NCH = 256-column chunks per row (3 for H <= 768: 72 instead of 96 partial-sum registers per lane, which together with
+// the launch bound keeps two 8-warp blocks per SM resident -- round 1 ran at 204 registers = one block = 12.5 % occupancy)
+template <typename DYT, typename XT, typename DXT, typename T, int NCH>
+__global__ void __launch_bounds__(LN_WARPS * 32, 2)
 layernorm_bwd_kernel(const DYT* __restrict__ dy, const XT* __restrict__ x, const T* __restrict__ res,
                      const float* __restrict__ gamma, const float* __restrict__ mean_in,
                      const float* __restrict__ rstd_in, long long rows, int H, uint64_t seed_in, uint32_t thresh_in,
@@ -347,19 +349,19 @@ layernorm_bwd_kernel(const DYT* __restrict__ dy, const XT* __restrict__ x, const
   bb::pdl_trigger();
   extern __shared__ float ln_part[];  // [2][LN_WARPS][H] per-warp partial dgamma / dbeta (no atomics, no conflicts)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float pg[LN_MAXCH][8], pb[LN_MAXCH][8], px[LN_MAXCH][8];
+  float pg[NCH][8], pb[NCH][8], px[NCH][8];
 #pragma unroll
-  for (int c = 0; c < LN_MAXCH; ++c)
+  for (int c = 0; c < NCH; ++c)
 #pragma unroll
     for (int j = 0; j < 8; ++j) pg[c][j] = pb[c][j] = px[c][j] = 0.f;
 
   for (long long row = blockIdx.x * (long long)LN_WARPS + warp; row < rows; row += (long long)gridDim.x * LN_WARPS) {
     const long long base = row * H;
     const float mean = mean_in[row], rstd = rstd_in[row];
-    float xh[LN_MAXCH][8], g[LN_MAXCH][8];
+    float xh[NCH][8], g[NCH][8];
     float c1 = 0.f, c2 = 0.f;
 #pragma unroll
-    for (int c = 0; c < LN_MAXCH; ++c) {
+    for (int c = 0; c < NCH; ++c) {
       const int col = c * 256 + lane * 8;
       if (col < H) {
         float z[8], d[8], gm[8];
@@ -391,7 +393,7 @@ layernorm_bwd_kernel(const DYT* __restrict__ dy, const XT* __restrict__ x, const
     c1 = warp_sum(c1) / (float)H;
     c2 = warp_sum(c2) / (float)H;
 #pragma unroll
-    for (int c = 0; c < LN_MAXCH; ++c) {
+    for (int c = 0; c < NCH; ++c) {
       const int col = c * 256 + lane * 8;
       if (col < H) {
         float dz[8];
@@ -415,7 +417,7 @@ layernorm_bwd_kernel(const DYT* __restrict__ dy, const XT* __restrict__ x, const
     float* sb = ln_part + LN_WARPS * H;
     float* sx = ln_part + 2 * LN_WARPS * H;
 #pragma unroll
-    for (int c = 0; c < LN_MAXCH; ++c) {
+    for (int c = 0; c < NCH; ++c) {
       const int col = c * 256 + lane * 8;
       if (col < H) {
         store8(sg + warp * H + col, pg[c]);
@@ -453,7 +455,20 @@ colsum_bf16_kernel(const T* __restrict__ x, long long rows, int N, long long ld,
   for (int j = 0; j < 8; ++j) acc[j] = 0.f;
   if (col < N) {
     const bool vec = (col + 8 <= N) && (ld % 8 == 0);
-    for (long long r = blockIdx.y * 8 + threadIdx.y; r < rows; r += (long long)gridDim.y * 8) {
+    const long long rstep = (long long)gridDim.y * 8;
+    long long r = blockIdx.y * 8 + threadIdx.y;
+    if (vec) {
+      for (; r + 3 * rstep < rows; r += 4 * rstep) {      // four independent 16-byte loads in flight per lane
+        float v0[8], v1[8], v2[8], v3[8];
+        load8(x + r * ld + col, v0);
+        load8(x + (r + rstep) * ld + col, v1);
+        load8(x + (r + 2 * rstep) * ld + col, v2);
+        load8(x + (r + 3 * rstep) * ld + col, v3);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += (v0[j] + v1[j]) + (v2[j] + v3[j]);
+      }
+    }
+    for (; r < rows; r += rstep) {
       if (vec) {
         float v[8];
         load8(x + r * ld + col, v);
@@ -837,12 +852,18 @@ extern "C" int bb_layernorm_bwd(const void* dy, int dy_f32, const void* x, int x
   do {                                                                                                              \
     static bool attr_done = false;                                                                                  \
     if (!attr_done) {                                                                                               \
-      cudaFuncSetAttribute(layernorm_bwd_kernel<DYT, XT, DXT, AT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304); \
+      cudaFuncSetAttribute(layernorm_bwd_kernel<DYT, XT, DXT, AT, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304); \
+      cudaFuncSetAttribute(layernorm_bwd_kernel<DYT, XT, DXT, AT, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304); \
       attr_done = true;                                                                                             \
     }                                                                                                               \
-    bb::launch_pdl(layernorm_bwd_kernel<DYT, XT, DXT, AT>, grid, LN_WARPS * 32, ln_smem, STREAM, (const DYT*)dy,    \
-                   (const XT*)x, (const AT*)residual, gamma, mean, rstd, rows, H, seed_in, thresh_in, scale_in,     \
-                   seed_out, thresh_out, scale_out, (DXT*)dx, (AT*)dres, dgamma, dbeta, dxsum);                     \
+    if (H <= 768)                                                                                                   \
+      bb::launch_pdl(layernorm_bwd_kernel<DYT, XT, DXT, AT, 3>, grid, LN_WARPS * 32, ln_smem, STREAM, (const DYT*)dy, \
+                     (const XT*)x, (const AT*)residual, gamma, mean, rstd, rows, H, seed_in, thresh_in, scale_in,   \
+                     seed_out, thresh_out, scale_out, (DXT*)dx, (AT*)dres, dgamma, dbeta, dxsum);                   \
+    else                                                                                                            \
+      bb::launch_pdl(layernorm_bwd_kernel<DYT, XT, DXT, AT, 4>, grid, LN_WARPS * 32, ln_smem, STREAM, (const DYT*)dy, \
+                     (const XT*)x, (const AT*)residual, gamma, mean, rstd, rows, H, seed_in, thresh_in, scale_in,   \
+                     seed_out, thresh_out, scale_out, (DXT*)dx, (AT*)dres, dgamma, dbeta, dxsum);                   \
   } while (0)
   if (bb::act_f32()) {
     if (dy_f32 && x_f32 && dx_f32) LN_BWD(float, float, float, float);
@@ -952,3 +973,5 @@ extern "C" int bb_softmax_xent(const float* logits, const int64_t* labels, int64
   count_launch();
   return check_launch("softmax_xent_kernel");
 }
+
+namespace bb { int set_salt_rowops(const unsigned long long* p) { return set_drop_salt_ptr_tu(p) == cudaSuccess ? 0 : -1; } }

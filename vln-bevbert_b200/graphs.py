@@ -1,0 +1,104 @@
+"""Whole-step CUDA-graph replay for the pre-training loop: forward + backward (+ gradient all-reduce) + optimizer of one
+(task, batch-shape) is captured once and replayed, so a step costs the host one `cudaGraphLaunch` instead of ~600 kernel
+launches plus the Python block / autograd glue (the step is host-bound otherwise: ~14.7 ms per step on a B200 whatever the
+kernels do).
+
+What makes a step replayable here:
+  * inputs live in STATIC device tensors (the caller refills them in place, e.g. from pinned host memory on a copy
+    stream -- bench.py's `dev_in` buffers); host-side index lists come from `ops.prepare_batch` (pinned tensors that
+    the captured copy nodes re-read);
+  * dropout seeds are kernel parameters frozen in the graph, so the per-step variation comes from the device-resident
+    salt every kernel XORs into its seed (`bb_set_drop_salt_ptr`): one 8-byte copy node at the head of the graph;
+  * the optimizer's host half (per-parameter step counters, bias-corrected step sizes, lr schedule) is redone before
+    each replay by `optim.AdamW.advance`; the graph re-uploads the pinned launch table and runs the update kernels;
+  * parameter gradients are carved from the per-step arena inside the graph's memory pool: same addresses every replay.
+A graph is keyed by (task, identity and shapes of the batch tensors).  Tasks whose forward needs a device->host
+synchronisation (sem / masksem: the number of labelled cells is computed on the device) run eagerly.
+"""
+import torch
+
+from . import blocks
+from . import kernels as K
+from . import _lib
+
+EAGER_TASKS = ("sem", "masksem")
+
+
+class GraphedTrainStep:
+    def __init__(self, net, optimizer, reduce_grads=None, warmup=2, loss_fn=None):
+        self.net, self.opt, self.reduce_grads, self.warmup = net, optimizer, reduce_grads, warmup
+        self.loss_fn = loss_fn or (lambda out: out.mean())
+        self.entries = {}
+        self.pool = None
+        dev = next(net.parameters()).device
+        self.salt_host = torch.zeros(1, dtype=torch.int64).pin_memory()
+        self.salt_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+        _lib.check(_lib.load().bb_set_drop_salt_ptr(self.salt_dev.data_ptr()), "bb_set_drop_salt_ptr")
+        self.nstep = 0
+        self.launches_per_replay = {}
+
+    @staticmethod
+    def _sig(batch, task):
+        return (task, id(batch)) + tuple((k, v.data_ptr(), tuple(v.shape)) for k, v in sorted(batch.items())
+                                         if torch.is_tensor(v))
+
+    def _eager(self, batch, task):
+        loss = self.loss_fn(self.net(batch, task))
+        loss.backward()
+        if self.reduce_grads is not None:
+            self.reduce_grads()
+        self.opt.step()
+        return loss.detach()
+
+    def _next_salt(self):
+        self.nstep += 1
+        self.salt_host[0] = blocks._mix64(self.nstep * 0x9E3779B97F4A7C15 + 12345) & 0x7FFFFFFFFFFFFFFF
+
+    def __call__(self, batch, task):
+        if task.startswith(EAGER_TASKS):
+            self._next_salt()
+            self.salt_dev.copy_(self.salt_host, non_blocking=True)
+            return self._eager(batch, task)
+        key = self._sig(batch, task)
+        ent = self.entries.get(key)
+        if ent is None:
+            ent = self.entries[key] = {"n": 0, "graph": None}
+        if ent["graph"] is None and ent["n"] < self.warmup:
+            ent["n"] += 1
+            self._next_salt()
+            self.salt_dev.copy_(self.salt_host, non_blocking=True)
+            return self._eager(batch, task)
+        if ent["graph"] is None:
+            self._capture(ent, batch, task)
+        else:
+            self._next_salt()
+            self.opt.advance(ent["sig"])
+            ent["graph"].replay()
+        return ent["loss"]
+
+    def _capture(self, ent, batch, task):
+        for p in self.net.parameters():
+            p.grad = None
+        torch.cuda.synchronize()
+        if self.pool is None:
+            self.pool = torch.cuda.graph_pool_handle()
+        g = torch.cuda.CUDAGraph()
+        self._next_salt()
+        n0 = K.launch_count()
+        with torch.cuda.graph(g, pool=self.pool):
+            self.salt_dev.copy_(self.salt_host, non_blocking=True)
+            loss = self.loss_fn(self.net(batch, task))
+            loss.backward()
+            if self.reduce_grads is not None:
+                self.reduce_grads()
+            self.opt.step()
+            ent["loss"] = loss.detach()
+        ent["launches"] = K.launch_count() - n0
+        ent["graph"], ent["sig"] = g, self.opt.last_sig
+        # the capture only RECORDED the step (and advanced the optimizer's host counters for it): run it once
+        g.replay()
+
+    def launches(self, batch, task):
+        """kernels of libbevbert_b200.so inside the captured step of (batch, task), or None when it runs eagerly."""
+        ent = self.entries.get(self._sig(batch, task))
+        return ent.get("launches") if ent and ent.get("graph") is not None else None

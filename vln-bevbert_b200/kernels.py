@@ -113,9 +113,22 @@ def gemm(a, b, out, M, N, K, lda, ldb, ldd, a_mn=False, b_mn=False, nb1=1, nb2=1
     return out
 
 
-def gemm_profile(enable: bool):
-    """Start / stop the library's per-launch GEMM timing (CUDA events around every tcgen05 GEMM launch)."""
-    _lib.check(_lib.load().bb_gemm_profile(int(enable)), "bb_gemm_profile")
+_PROF_BUF = None
+
+
+def gemm_profile(enable: bool, capacity: int = 8192):
+    """Start / stop the library's per-launch GEMM timing: every tcgen05 GEMM launch stamps %globaltimer (first CTA
+    start, last CTA end) into its slot of a device buffer -- no events between launches."""
+    global _PROF_BUF
+    lib = _lib.load()
+    if enable:
+        if _PROF_BUF is None or _PROF_BUF.shape[0] < capacity:
+            _PROF_BUF = torch.empty(capacity, 2, dtype=torch.int64, device="cuda")
+        _PROF_BUF[:, 0] = -1          # all ones = "no start yet" for the unsigned atomicMin
+        _PROF_BUF[:, 1] = 0
+        torch.cuda.synchronize()
+        _lib.check(lib.bb_gemm_profile_buffer(_PROF_BUF.data_ptr(), _PROF_BUF.shape[0]), "bb_gemm_profile_buffer")
+    _lib.check(lib.bb_gemm_profile(int(enable)), "bb_gemm_profile")
 
 
 def gemm_profile_records():

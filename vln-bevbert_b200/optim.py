@@ -64,6 +64,7 @@ class AdamW:
         self._sumsq = None
         self._tables = {}       # gradient signature -> (MtTable, [flat index], shadow entries fully covered)
         self.grad_norm = None   # 0-d device tensor of the last step (pre-clip total norm), when clipping is on
+        self.last_sig = None
 
     # ------------------------------------------------------------------ state
     def _init_state(self):
@@ -120,6 +121,31 @@ class AdamW:
         self._tables[sig] = ent
         return ent
 
+    def _fill(self, tab, idx, sig, with_grads):
+        """host half of a step: advance the per-parameter step counters and write step size / decay (and, outside
+        graph replay, the gradient pointers) into the pinned launch table.  -> False when the table is out of date."""
+        rows = tab.np
+        for r, i in enumerate(idx):
+            gi, p = self.flat[i]
+            grp = self.param_groups[gi]
+            if with_grads:
+                g = p.grad
+                if g.dtype != torch.float32 or not g.is_contiguous():
+                    g = p.grad = g.float().contiguous()
+                if rows["p"][r] != p.data_ptr():      # storage moved (module.to(), bias re-homing): rebuild the table
+                    for j in idx[:r]:
+                        self.steps[j] -= 1
+                    self._tables.pop(sig, None)
+                    return False
+                rows["g"][r] = g.data_ptr()
+            self.steps[i] += 1
+            t = self.steps[i]
+            lr = grp["lr"]
+            b1, b2 = grp["betas"]
+            rows["step_size"][r] = lr * math.sqrt(1.0 - b2 ** t) / (1.0 - b1 ** t) if grp["correct_bias"] else lr
+            rows["decay"][r] = lr * grp["weight_decay"]
+        return True
+
     @torch.no_grad()
     def step(self, grad_scale=1.0, set_to_none=True):
         sig = tuple(i for i, (_, p) in enumerate(self.flat) if p.grad is not None)
@@ -128,25 +154,8 @@ class AdamW:
         if self.m is None:
             self._init_state()
         tab, idx, stale, _ = self._table(sig)
-        rows = tab.np
-        for r, i in enumerate(idx):
-            gi, p = self.flat[i]
-            g = p.grad
-            if g.dtype != torch.float32 or not g.is_contiguous():
-                g = p.grad = g.float().contiguous()
-            grp = self.param_groups[gi]
-            self.steps[i] += 1
-            t = self.steps[i]
-            lr = grp["lr"]
-            b1, b2 = grp["betas"]
-            ss = lr * math.sqrt(1.0 - b2 ** t) / (1.0 - b1 ** t) if grp["correct_bias"] else lr
-            if rows["p"][r] != p.data_ptr():      # storage moved (module.to(), bias re-homing): rebuild the table
-                self._tables.pop(sig, None)
-                self.steps = [st - (1 if j in idx[:r + 1] else 0) for j, st in enumerate(self.steps)]
-                return self.step(grad_scale, set_to_none)
-            rows["g"][r] = g.data_ptr()
-            rows["step_size"][r] = ss
-            rows["decay"][r] = lr * grp["weight_decay"]
+        if not self._fill(tab, idx, sig, True):
+            return self.step(grad_scale, set_to_none)
         tab.upload()
         b1, b2 = self.param_groups[0]["betas"]
         eps = self.param_groups[0]["eps"]
@@ -160,7 +169,14 @@ class AdamW:
         if set_to_none:
             for i in idx:
                 self.flat[i][1].grad = None
+        self.last_sig = sig
         return self.grad_norm
+
+    def advance(self, sig):
+        """CUDA-graph replay of a captured step(): the graph re-uploads the pinned table and re-launches the kernels;
+        only the host half (step counters, bias-corrected step sizes, current lr) has to be redone before the replay."""
+        tab, idx, _, _ = self._tables[sig]
+        self._fill(tab, idx, sig, False)
 
     def total_grad_norm(self):
         """sqrt of the device-side sum of squares of the last clipped step (0-d tensor, no sync)."""
