@@ -124,6 +124,10 @@ int bb_bev_scatter_mean_bf16(const void* feats_bf16, const int32_t* cell_idx, in
  * sem_mask u8 (B, D*D) = (sum over classes > 0). */
 int bb_bev_scatter_sem_f64(const double* sems, const int32_t* cell_idx, int B, int P, int S, int ncell,
                            double* bev_sem, uint8_t* sem_mask, void* stream);
+/* Same result from the labels as stored on disk: sem_ids u8 (B, P) class ids in [0, S) (the one-hot expansion of
+ * pretrain_src/data/dataset.py:402 never leaves the host).  bev_sem f64 (B, D*D, S) in {0, 1}, sem_mask u8 (B, D*D). */
+int bb_bev_scatter_sem_u8(const uint8_t* sem_ids, const int32_t* cell_idx, int B, int P, int S, int ncell, double* bev_sem,
+                          uint8_t* sem_mask, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Row kernels (coalesced, vectorised, warp reductions; fp32 math, bf16 storage).

@@ -197,8 +197,10 @@ def bev_scatter_mean(feats, cell_idx, ncell, want_f32=True, want_bf16=True):
     return (out if want_f32 else None), (_a(out) if want_bf16 else None), ob, cnt.to(torch.int32)
 
 
-def bev_scatter_sem(sems, cell_idx, ncell):
+def bev_scatter_sem(sems, cell_idx, ncell, num_classes=40):
     from oracle import bevbert_ref as R
+    if sems.dtype == torch.uint8:
+        sems = torch.nn.functional.one_hot(sems.long(), num_classes).to(torch.float64)
     out = torch.stack([R.scatter_mean(sems[i], cell_idx[i].long(), ncell) for i in range(sems.shape[0])], 0)
     out[out > 0] = 1
     return out, out.sum(2) > 0

@@ -150,6 +150,29 @@ def test_layernorm_fwd_bwd(K, x_f32, res):
     assert float((dxs.cpu() - rdx.sum(0)).norm()) < 1e-3 * float(rdx.abs().sum(0).norm())   # bias grad of the dense before LN
 
 
+def _ln_keep_mask(seed, rows, H, thresh):
+    """torch restatement of the LayerNorm-site dropout decisions (csrc/rowops.cu ln_keep8: one hash per 8-element vector,
+    four mixes, 16-bit halves), for checking that forward and backward apply the documented function."""
+    M = 0xFFFFFFFF
+    vec = torch.arange(rows * H // 8, dtype=torch.int64)
+    x = (vec & M) ^ (((vec >> 32) * 0x9E3779B1) & M) ^ (seed & M) ^ (((seed >> 32) * 0x85EBCA6B) & M)
+    x = x ^ (x >> 16)
+    x = (x * 0x7FEB352D) & M
+    x = x ^ (x >> 15)
+    x = (x * 0x846CA68B) & M
+    h = x ^ (x >> 16)
+    t16 = thresh >> 16
+    keep = torch.zeros(rows * H // 8, 8, dtype=torch.bool)
+    for k in range(4):
+        y = (h + (k + 1) * 0x9E3779B1) & M
+        y = y ^ (y >> 15)
+        y = (y * 0x2C1B3C6D) & M
+        y = y ^ (y >> 16)
+        keep[:, 2 * k] = (y & 0xFFFF) >= t16
+        keep[:, 2 * k + 1] = (y >> 16) >= t16
+    return keep.reshape(rows, H)
+
+
 def test_layernorm_dropout_replay(K):
     rows, H = 512, 768
     x, r = rnd(rows, H), rnd(rows, H, seed=1)
@@ -159,11 +182,18 @@ def test_layernorm_dropout_replay(K):
     y, _, mean, rstd = K.layernorm_fwd(dev(x), dev(r), dev(gam), dev(bet), 1e-12, drop_in=di, drop_out=do)
     out_keep = (y.cpu().float() != 0)
     assert abs(float(out_keep.float().mean()) - 0.9) < 5e-3
+    assert torch.equal(out_keep | (y.cpu().float() == 0), _ln_keep_mask(78, rows, H, th) | (y.cpu().float() == 0))
+    assert (out_keep & ~_ln_keep_mask(78, rows, H, th)).sum() == 0          # nothing the documented mask drops survives
     # backward with dy = 1 : dx must vanish exactly where the input mask dropped x
-    xin = K.dropout_act(dev(x), di).cpu().float()
     dy = torch.ones(rows, H).to(BF)
     dx, dres = K.layernorm_bwd(dev(dy), dev(x), dev(r), dev(gam), mean, rstd, drop_in=di, drop_out=do, want_dres=True)
-    dropped = (xin == 0) & (x.float() != 0)
+    dropped = ~_ln_keep_mask(77, rows, H, th)
+    assert abs(float(dropped.float().mean()) - 0.1) < 5e-3
+    # the forward used the same input mask: recompute LN(drop(x) + r) on the host from the documented mask
+    z = x.float() * (~dropped).float() * sc + r.float()
+    yref = ((z - z.mean(1, keepdim=True)) / torch.sqrt(z.var(1, unbiased=False, keepdim=True) + 1e-12)) * sc
+    live = _ln_keep_mask(78, rows, H, th)
+    assert rel_l2(y.cpu().float()[live], yref[live]) < 1e-2
     assert float(dx.cpu().float()[dropped].abs().max()) == 0.0
     kept = ~dropped
     assert torch.allclose(dx.cpu().float()[kept], (dres.cpu().float() * sc)[kept], rtol=2e-2, atol=1e-3)

@@ -210,3 +210,43 @@ def test_bf16_wire_format_matches_fp32_inputs():
             outs.append((float(loss), g.clone()))
         assert abs(outs[0][0] - outs[1][0]) <= 1e-2 * abs(outs[0][0])
         assert rel_l2(outs[1][1], outs[0][1]) < 5e-2
+
+
+@pytest.mark.parametrize("task", ["sap", "masksem"])
+def test_wire_format_matches_oracle_and_is_exact_for_labels(task):
+    """16-bit wire format (ops.prepare_batch(wire_dtype=bf16): bf16 grid / view features + uint8 semantic class ids
+    instead of float64 one-hots) against the ORACLE fed with the same (bf16-rounded) features: the pooled label map and
+    masks are bit-identical to the one-hot path, loss and gradients stay inside the bf16 bars."""
+    from bevbert_b200.model.ops import prepare_batch
+    cfg, scfg = small_config(), small_synth()
+    model = synth.det_init_(GlocalTextPathCMTPreTraining(cfg), seed=3).to(DEV).train()
+    host = synth.make_batch(scfg, seed=21, task=task)
+    wired = prepare_batch(synth.clone_batch(host), wire_dtype=torch.bfloat16)
+    assert wired["sems"].dtype == torch.uint8 and wired["rgbs"].dtype == torch.bfloat16
+    dev_b = synth.batch_to(wired, DEV)
+    with torch.no_grad():
+        a = model.lift_splat(dict(dev_b))
+        b = model.lift_splat(dict(synth.batch_to(synth.clone_batch(host), DEV)))
+    assert torch.equal(a["bev_sems"], b["bev_sems"]) and torch.equal(a["bev_sem_masks"], b["bev_sem_masks"])
+    assert a["bev_sems"].dtype == torch.float64
+    out = model(dev_b, task)
+    out.mean().backward()
+    rounded = synth.clone_batch(host)
+    for k in ("rgbs", "traj_view_img_fts"):
+        rounded[k] = rounded[k].to(torch.bfloat16).float()
+    sd = {k: v.detach().float().cpu().clone().requires_grad_(True) for k, v in model.state_dict().items()}
+    ref, rg = _oracle_grads(sd, rounded, task, cfg)
+    names = [n for n, _ in model.named_parameters()]
+    errs, glob = grad_errors({n: p.grad for n, p in model.named_parameters()}, {n: rg.get(n) for n in names})
+    print("wire format task=%s loss rel-L2 %.3e all-grads rel-L2 %.3e" % (task, rel_l2(out, ref), glob))
+    assert rel_l2(out, ref) < 1e-2 and glob < GLOBAL_GRAD_BAR[task]
+
+
+@pytest.mark.parametrize("task", ["mlm", "sap"])
+def test_rxr_config_long_instruction_xlmr_vocab(task):
+    """BASELINE.json configs[3] at reduced depth / batch: XLM-R vocabulary (250002 rows, tied MLM decoder = a 250k-wide
+    vocab GEMM + cross-entropy), 514 positions, 512-token instructions -- the 512-key language self-attention and the
+    512-key / 121-query cross-attention run through the tcgen05 attention kernels (8 key blocks), configs/rxr_model.json:20,30."""
+    cfg = small_config(vocab_size=250002, max_position_embeddings=514)
+    scfg = small_synth(txt_len=512, vocab_lo=1000, vocab_hi=250000, n_mask_tokens=40)
+    _compare(task, cfg, scfg, seed=5)

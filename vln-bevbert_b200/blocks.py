@@ -1073,6 +1073,16 @@ def to_f32(x):
 
 # =============================================================================================== autograd glue
 DIRECT_PARAM_GRADS = False   # parallel.direct_param_grads(): blocks assign p.grad themselves
+AFTER_BLOCK_BWD = None       # parallel.FlatGradAllReduce: called after every block's backward (overlapped reduction)
+DEFER_GRAD_ADDS = False      # a second contribution to a parameter waits in PENDING_ADDS until the reductions are done
+PENDING_ADDS = []
+
+
+def apply_pending_adds():
+    for p, g in PENDING_ADDS:
+        p.grad.add_(g)
+    PENDING_ADDS.clear()
+
 
 
 class _BlockFn(torch.autograd.Function):
@@ -1101,8 +1111,12 @@ class _BlockFn(torch.autograd.Function):
                         g = g.contiguous()
                     if p.grad is None:
                         p.grad = g
+                    elif DEFER_GRAD_ADDS:
+                        PENDING_ADDS.append((p, g))
                     else:
                         p.grad.add_(g)
+            if AFTER_BLOCK_BWD is not None:
+                AFTER_BLOCK_BWD()
             full = [g if n else None for g, n in zip(gin, needs)] + [None] * len(ctx.params)
             return (None, None, *full)
         full = list(gin) + list(gpar)

@@ -776,11 +776,11 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
       const uint32_t idesc_s = umma_idesc_bf16(BM, 128, 0, 0);
       const uint32_t idesc_acc = MODE == 0 ? umma_idesc_bf16(BM, 64, 0, 1) : umma_idesc_bf16(BM, 64, 1, 1);
       const uint32_t aR0 = smem_u32(sR0), aR1 = smem_u32(sR1), aPD = smem_u32(sPD), aDS = smem_u32(sDS);
-      mbar_wait(r_full, 0);
+      mbar_wait_relaxed(r_full, 0);
       // accumulate the products of tile t (its Pdrop / dS are in shared memory, its streamed operands in stage t & 1)
       auto issue_acc = [&](int t) {
         const uint32_t a0 = smem_u32(sST + (t & 1) * 2 * TILE_BYTES), a1 = a0 + TILE_BYTES;
-        mbar_wait(ds_full, t & 1);
+        mbar_wait_relaxed(ds_full, t & 1);
         tc_fence_after();
         if (MODE == 0) {
           // dQ += dS K_j : A = dS K-major (two 64-key blocks), B = K_j [key][d] as MN-major (N = d, K = key)
@@ -804,8 +804,8 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
       };
       for (int tile = 0; tile < ntiles; ++tile) {
         const int s = tile & 1;
-        mbar_wait(&st_full[s], (tile >> 1) & 1);
-        if (tile > 0) mbar_wait(sdp_empty, (tile - 1) & 1);   // the softmax warps hold S / dP of tile-1 in registers
+        mbar_wait_relaxed(&st_full[s], (tile >> 1) & 1);
+        if (tile > 0) mbar_wait_relaxed(sdp_empty, (tile - 1) & 1);   // the softmax warps hold S / dP of tile-1 in registers
         tc_fence_after();
         const uint32_t a0 = smem_u32(sST + s * 2 * TILE_BYTES), a1 = a0 + TILE_BYTES;
         // S = Q K^T and dP = dO V^T (both operands K-major, N = 128)
@@ -825,7 +825,7 @@ attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
         // while the softmax warps work on this tile: finish the previous one and fetch the next
         if (tile > 0) issue_acc(tile - 1);
         if (tile + 1 < ntiles) {
-          if (tile >= 1) mbar_wait(&st_empty[s ^ 1], ((tile - 1) >> 1) & 1);
+          if (tile >= 1) mbar_wait_relaxed(&st_empty[s ^ 1], ((tile - 1) >> 1) & 1);
           load_stage(tile + 1);
         }
       }

@@ -301,6 +301,49 @@ extern "C" int bb_bev_scatter_mean_bf16(const void* feats, const int32_t* cell_i
                              ob_mask, counts, stream);
 }
 
+// Semantic labels as stored on disk: one uint8 class id per point (the reference expands them to float64 one-hots on
+// the host, pretrain_src/data/dataset.py:117,402, and ships 24 MB per 32-sample batch across PCIe).  The pooled label
+// map is binary (mean of one-hots, then sem[sem > 0] = 1, bev_utils.py:417-423): class c is set in a cell iff at least
+// one kept point of class c falls into it -- one 64-bit presence mask per cell, built with shared-memory atomicOr.
+__global__ void __launch_bounds__(256)
+scatter_sem_u8_kernel(const uint8_t* __restrict__ sem_ids, const int32_t* __restrict__ cell_idx, int P, int S, int ncell,
+                      double* __restrict__ bev_sem, uint8_t* __restrict__ sem_mask) {
+  bb::pdl_wait();
+  bb::pdl_trigger();
+  extern __shared__ unsigned long long bits[];
+  const int b = blockIdx.x;
+  for (int i = threadIdx.x; i < ncell; i += blockDim.x) bits[i] = 0ull;
+  __syncthreads();
+  const uint8_t* ids = sem_ids + (long long)b * P;
+  const int32_t* idx = cell_idx + (long long)b * P;
+  for (int i = threadIdx.x; i < P; i += blockDim.x) {
+    const int c = idx[i];
+    const int k = ids[i];
+    if (c >= 0 && c < ncell && k < S) atomicOr(&bits[c], 1ull << k);
+  }
+  __syncthreads();
+  double* out = bev_sem + (long long)b * ncell * S;
+  for (int i = threadIdx.x; i < ncell * S; i += blockDim.x) {
+    const int cell = i / S, k = i - cell * S;
+    out[i] = (bits[cell] >> k) & 1ull ? 1.0 : 0.0;
+  }
+  if (sem_mask)
+    for (int i = threadIdx.x; i < ncell; i += blockDim.x) sem_mask[(long long)b * ncell + i] = bits[i] != 0ull;
+}
+
+extern "C" int bb_bev_scatter_sem_u8(const uint8_t* sem_ids, const int32_t* cell_idx, int B, int P, int S, int ncell,
+                                     double* bev_sem, uint8_t* sem_mask, void* stream) {
+  using namespace bb;
+  if (!sem_ids || !cell_idx || !bev_sem) return set_error("bb_bev_scatter_sem_u8: null argument");
+  if (S > 64) return set_error("bb_bev_scatter_sem_u8: at most 64 classes");
+  if ((size_t)ncell * 8 > 48 * 1024) return set_error("bb_bev_scatter_sem_u8: too many cells for shared memory");
+  if (B <= 0) return 0;
+  bb::launch_pdl(scatter_sem_u8_kernel, (unsigned)B, 256, (size_t)ncell * 8, (cudaStream_t)stream, sem_ids, cell_idx, P, S,
+                 ncell, bev_sem, sem_mask);
+  count_launch();
+  return check_launch("scatter_sem_u8_kernel");
+}
+
 extern "C" int bb_bev_scatter_sem_f64(const double* sems, const int32_t* cell_idx, int B, int P, int S, int ncell,
                                       double* bev_sem, uint8_t* sem_mask, void* stream) {
   using namespace bb;

@@ -262,6 +262,52 @@ __global__ void axpy_f32_from_bf16_kernel(const T* __restrict__ x, float* __rest
 constexpr int LN_MAXCH = 4;  // 4 chunks of 256 columns -> H <= 1024
 constexpr int LN_WARPS = 8;
 
+// Dropout decisions of the LayerNorm sites, one 8-bit keep mask per 8-element vector: a full hash of (seed, vector
+// index) and four cheap mixes whose 16-bit halves decide two elements each (keep iff half >= thresh >> 16) -- 4.5
+// integer instructions per element instead of a 12-instruction hash each (the backward kernel executed 70 instructions
+// per element in round 1, most of them the two per-element hashes).  Forward and backward evaluate the same function.
+__device__ __forceinline__ uint32_t ln_keep8(uint64_t seed, long long elem0, uint32_t thresh) {
+  const uint32_t h = rng_u32(seed, (uint64_t)(elem0 >> 3));
+  const uint32_t t16s = thresh & 0xFFFF0000u;
+  uint32_t bits = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    uint32_t x = h + (uint32_t)(k + 1) * 0x9E3779B1u;
+    x ^= x >> 15;
+    x *= 0x2C1B3C6Du;
+    x ^= x >> 16;
+    bits |= ((x << 16) >= t16s ? 1u : 0u) << (2 * k);
+    bits |= (x >= t16s ? 1u : 0u) << (2 * k + 1);
+  }
+  return bits;
+}
+// raw 8-element vectors (kept packed while they wait in registers for the next row)
+template <typename T> struct Raw8;
+template <> struct Raw8<bf16> {
+  uint4 v;
+  __device__ __forceinline__ void load(const bf16* p) { v = __ldg(reinterpret_cast<const uint4*>(p)); }
+  __device__ __forceinline__ void unpack(float (&f)[8]) const {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 t = __bfloat1622float2(h[i]);
+      f[2 * i] = t.x;
+      f[2 * i + 1] = t.y;
+    }
+  }
+};
+template <> struct Raw8<float> {
+  float4 a, b;
+  __device__ __forceinline__ void load(const float* p) {
+    a = __ldg(reinterpret_cast<const float4*>(p));
+    b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  }
+  __device__ __forceinline__ void unpack(float (&f)[8]) const {
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w;
+    f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+  }
+};
+
 template <typename XT, typename T>
 __global__ void __launch_bounds__(LN_WARPS * 32)
 layernorm_fwd_kernel(const XT* __restrict__ x, const T* __restrict__ res, const float* __restrict__ gamma,
@@ -283,8 +329,9 @@ layernorm_fwd_kernel(const XT* __restrict__ x, const T* __restrict__ res, const 
     if (col < H) {
       load8(x + base + col, z[c]);
       if (thresh_in) {
+        const uint32_t keep = ln_keep8(seed_in, base + col, thresh_in);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) z[c][j] = drop_keep(seed_in, base + col + j, thresh_in) ? z[c][j] * scale_in : 0.f;
+        for (int j = 0; j < 8; ++j) z[c][j] = (keep >> j) & 1u ? z[c][j] * scale_in : 0.f;
       }
       if (res) {
         float r[8];
@@ -322,10 +369,11 @@ layernorm_fwd_kernel(const XT* __restrict__ x, const T* __restrict__ res, const 
       float g[8], b[8], o[8];
       load8(gamma + col, g);
       load8(beta + col, b);
+      const uint32_t keep = thresh_out ? ln_keep8(seed_out, base + col, thresh_out) : 0xFFu;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         o[j] = (z[c][j] - mean) * rstd * g[j] + b[j];
-        if (thresh_out) o[j] = drop_keep(seed_out, base + col + j, thresh_out) ? o[j] * scale_out : 0.f;
+        if (thresh_out) o[j] = (keep >> j) & 1u ? o[j] * scale_out : 0.f;
       }
       if (y) store8(y + base + col, o);
       if (y_f32) store8(y_f32 + base + col, o);
@@ -333,12 +381,13 @@ layernorm_fwd_kernel(const XT* __restrict__ x, const T* __restrict__ res, const 
   }
 }
 
-// Backward. Grid-stride over rows (one warp per row); each lane keeps per-column dgamma/dbeta partials,
-// reduced through shared memory and flushed with one atomicAdd per column per block.
-// NCH = 256-column chunks per row (3 for H <= 768: 72 instead of 96 partial-sum registers per lane, which together with
-// the launch bound keeps two 8-warp blocks per SM resident -- round 1 ran at 204 registers = one block = 12.5 % occupancy)
+// Backward.  Grid-stride over rows, one warp per row; each lane keeps per-column dgamma / dbeta / dxsum partials in
+// registers (reduced through shared memory, one atomicAdd per column per block).  NCH = 256-column chunks per row (3 for
+// H <= 768).  The three input vectors of the NEXT row are loaded (kept packed) before the current row is processed, so
+// every warp has two rows of loads in flight: the round-1 kernel stalled on the load -> reduce -> store chain of a
+// single row (ncu: long-scoreboard stalls on the first use of each loaded vector, 0.24 of the HBM peak).
 template <typename DYT, typename XT, typename DXT, typename T, int NCH>
-__global__ void __launch_bounds__(LN_WARPS * 32, 2)
+__global__ void __launch_bounds__(LN_WARPS * 32)
 layernorm_bwd_kernel(const DYT* __restrict__ dy, const XT* __restrict__ x, const T* __restrict__ res,
                      const float* __restrict__ gamma, const float* __restrict__ mean_in,
                      const float* __restrict__ rstd_in, long long rows, int H, uint64_t seed_in, uint32_t thresh_in,
@@ -347,42 +396,74 @@ layernorm_bwd_kernel(const DYT* __restrict__ dy, const XT* __restrict__ x, const
                      float* __restrict__ dxsum) {
   bb::pdl_wait();
   bb::pdl_trigger();
-  extern __shared__ float ln_part[];  // [2][LN_WARPS][H] per-warp partial dgamma / dbeta (no atomics, no conflicts)
+  extern __shared__ float ln_part[];  // [3][LN_WARPS][H] per-warp partial dgamma / dbeta / dxsum
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float pg[NCH][8], pb[NCH][8], px[NCH][8];
 #pragma unroll
   for (int c = 0; c < NCH; ++c)
 #pragma unroll
     for (int j = 0; j < 8; ++j) pg[c][j] = pb[c][j] = px[c][j] = 0.f;
+  float gm[NCH][8];
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    const int col = c * 256 + lane * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) gm[c][j] = 0.f;
+    if (col < H) load8(gamma + col, gm[c]);
+  }
 
-  for (long long row = blockIdx.x * (long long)LN_WARPS + warp; row < rows; row += (long long)gridDim.x * LN_WARPS) {
-    const long long base = row * H;
-    const float mean = mean_in[row], rstd = rstd_in[row];
-    float xh[NCH][8], g[NCH][8];
-    float c1 = 0.f, c2 = 0.f;
+  const long long rstep = (long long)gridDim.x * LN_WARPS;
+  long long row = blockIdx.x * (long long)LN_WARPS + warp;
+  Raw8<XT> nx[NCH];
+  Raw8<T> nr[NCH];
+  Raw8<DYT> nd[NCH];
+  float nmean = 0.f, nrstd = 0.f;
+  auto fetch = [&](long long r) {
+    const long long b = r * H;
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
       const int col = c * 256 + lane * 8;
       if (col < H) {
-        float z[8], d[8], gm[8];
-        load8(x + base + col, z);
-        if (thresh_in) {
+        nx[c].load(x + b + col);
+        if (res) nr[c].load(res + b + col);
+        nd[c].load(dy + b + col);
+      }
+    }
+    nmean = mean_in[r];
+    nrstd = rstd_in[r];
+  };
+  if (row < rows) fetch(row);
+  for (; row < rows; row += rstep) {
+    const long long base = row * H;
+    const float mean = nmean, rstd = nrstd;
+    float xh[NCH][8], g[NCH][8];
+    uint32_t keep_in[NCH];
+    float c1 = 0.f, c2 = 0.f;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) z[j] = drop_keep(seed_in, base + col + j, thresh_in) ? z[j] * scale_in : 0.f;
+    for (int c = 0; c < NCH; ++c) {
+      const int col = c * 256 + lane * 8;
+      keep_in[c] = 0xFFu;
+      if (col < H) {
+        float z[8], d[8];
+        nx[c].unpack(z);
+        if (thresh_in) {
+          keep_in[c] = ln_keep8(seed_in, base + col, thresh_in);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) z[j] = (keep_in[c] >> j) & 1u ? z[j] * scale_in : 0.f;
         }
         if (res) {
           float r[8];
-          load8(res + base + col, r);
+          nr[c].unpack(r);
 #pragma unroll
           for (int j = 0; j < 8; ++j) z[j] += r[j];
         }
-        load8(dy + base + col, d);
-        load8(gamma + col, gm);
+        nd[c].unpack(d);
+        const uint32_t keep_out = thresh_out ? ln_keep8(seed_out, base + col, thresh_out) : 0xFFu;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          if (thresh_out) d[j] = drop_keep(seed_out, base + col + j, thresh_out) ? d[j] * scale_out : 0.f;
+          if (thresh_out) d[j] = (keep_out >> j) & 1u ? d[j] * scale_out : 0.f;
           xh[c][j] = (z[j] - mean) * rstd;
-          g[c][j] = d[j] * gm[j];
+          g[c][j] = d[j] * gm[c][j];
           c1 += g[c][j];
           c2 += g[c][j] * xh[c][j];
           pg[c][j] += d[j] * xh[c][j];
@@ -390,6 +471,7 @@ layernorm_bwd_kernel(const DYT* __restrict__ dy, const XT* __restrict__ x, const
         }
       }
     }
+    if (row + rstep < rows) fetch(row + rstep);      // next row's loads fly during the reductions and stores below
     c1 = warp_sum(c1) / (float)H;
     c2 = warp_sum(c2) / (float)H;
 #pragma unroll
@@ -403,7 +485,7 @@ layernorm_bwd_kernel(const DYT* __restrict__ dy, const XT* __restrict__ x, const
         if (dx || dxsum) {
           if (thresh_in) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) dz[j] = drop_keep(seed_in, base + col + j, thresh_in) ? dz[j] * scale_in : 0.f;
+            for (int j = 0; j < 8; ++j) dz[j] = (keep_in[c] >> j) & 1u ? dz[j] * scale_in : 0.f;
           }
           if (dx) store8(dx + base + col, dz);
 #pragma unroll
@@ -845,7 +927,7 @@ extern "C" int bb_layernorm_bwd(const void* dy, int dy_f32, const void* x, int x
   if (rows <= 0) return 0;
   if (H % 8 != 0 || H > LN_MAXCH * 256) return set_error("bb_layernorm_bwd: H must be a multiple of 8 and <= 1024");
   long long g = (rows + LN_WARPS - 1) / LN_WARPS;
-  if (g > 148 * 2) g = 148 * 2;
+  if (g > 148) g = 148;   // one resident block per SM (233 registers), rows grid-strided
   const unsigned grid = (unsigned)g;
   const size_t ln_smem = (size_t)3 * LN_WARPS * H * sizeof(float);
 #define LN_BWD(DYT, XT, DXT, AT)                                                                                    \

@@ -68,8 +68,24 @@ class GraphedTrainStep:
             self._next_salt()
             self.salt_dev.copy_(self.salt_host, non_blocking=True)
             return self._eager(batch, task)
+        if ent["graph"] is None and ent.get("failed"):
+            self._next_salt()
+            self.salt_dev.copy_(self.salt_host, non_blocking=True)
+            return self._eager(batch, task)
         if ent["graph"] is None:
-            self._capture(ent, batch, task)
+            try:
+                self._capture(ent, batch, task)
+            except Exception as e:          # e.g. a host sync inside forward: this (task, batch) stays eager
+                import warnings
+                warnings.warn("CUDA-graph capture of the %s step failed (%s: %s); running it eagerly" % (
+                    task, type(e).__name__, str(e)[:200]))
+                torch.cuda.synchronize()
+                ent["failed"] = True
+                for p in self.net.parameters():
+                    p.grad = None
+                self._next_salt()
+                self.salt_dev.copy_(self.salt_host, non_blocking=True)
+                return self._eager(batch, task)
         else:
             self._next_salt()
             self.opt.advance(ent["sig"])

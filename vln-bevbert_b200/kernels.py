@@ -324,8 +324,18 @@ def bev_scatter_mean(feats, cell_idx, ncell, want_f32=True, want_bf16=True):
     return o32, o16, ob.bool(), cnt
 
 
-def bev_scatter_sem(sems, cell_idx, ncell):
+def bev_scatter_sem(sems, cell_idx, ncell, num_classes=40):
+    """sems: float64 one-hots (B,P,S) as the reference collates them, or uint8 class ids (B,P) (wire format)."""
     lib = _lib.load()
+    if sems.dtype == torch.uint8:
+        if not sems.is_cuda:
+            raise RuntimeError("sems must be a CUDA tensor (the hot path has no CPU implementation)")
+        B, P = sems.shape
+        out = torch.empty(B, ncell, num_classes, dtype=torch.float64, device=sems.device)
+        m = torch.empty(B, ncell, dtype=torch.uint8, device=sems.device)
+        _lib.check(lib.bb_bev_scatter_sem_u8(sems.contiguous().data_ptr(), cell_idx.data_ptr(), B, P, num_classes, ncell,
+                                             out.data_ptr(), m.data_ptr(), _stream()), "bb_bev_scatter_sem_u8")
+        return out, m.bool()
     _req(sems, torch.float64, "sems")
     B, P, S = sems.shape
     out = torch.empty(B, ncell, S, dtype=torch.float64, device=sems.device)

@@ -136,6 +136,14 @@ def prepare_batch(batch, wire_dtype=None):
             if torch.is_tensor(v) and v.dtype == torch.float32:
                 v = v.to(wire_dtype)
                 out[k] = v.pin_memory() if pin else v
+        # semantic labels: the float64 one-hots of dataset.py:402 back to the uint8 class ids they were built from
+        # (lossless when every row is exactly one-hot, which is how the reference constructs them)
+        sem = out.get("sems")
+        if torch.is_tensor(sem) and sem.dtype == torch.float64 and sem.dim() == 3 and sem.shape[-1] <= 64:
+            ids = sem.argmax(-1)
+            if bool((sem.sum(-1) == 1).all()) and bool((sem.gather(-1, ids[..., None]) == 1).all()):
+                ids = ids.to(torch.uint8)
+                out["sems"] = ids.pin_memory() if pin else ids
     return out
 
 

@@ -102,8 +102,10 @@ class GlocalTextPathCMTPreTraining(PreTrainedBase):
         bs = rgbs.shape[0]
         D = self.config.bev_dim
         idx, _ = self.projector.lift_index(depths, T_c2w, S_w2c, T_w2c, depth_scale=10.0)
-        bev, _, ob, bsem, bsem_mask = self.projector.splat(idx, rgbs.reshape(bs, -1, rgbs.shape[-1]),
-                                                           sems.reshape(bs, -1, sems.shape[-1]))
+        # sems: float64 one-hots (B, 2352, 40) as collated by the reference, or the uint8 class ids (B, 2352) they were
+        # expanded from (ops.prepare_batch wire format)
+        sems = sems.reshape(bs, -1) if sems.dtype == torch.uint8 else sems.reshape(bs, -1, sems.shape[-1])
+        bev, _, ob, bsem, bsem_mask = self.projector.splat(idx, rgbs.reshape(bs, -1, rgbs.shape[-1]), sems)
         if self.bev_pos_fts.device != bev.device:
             self.bev_pos_fts = self.bev_pos_fts.to(bev.device)
         pos = torch.cat([gpos.expand(-1, D * D, -1), self.bev_pos_fts.expand(bs, -1, -1)], dim=-1)

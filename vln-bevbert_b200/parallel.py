@@ -17,52 +17,110 @@ _CHECK_LAYOUT = os.environ.get("BEVBERT_CHECK_ARENA") == "1"
 
 
 class FlatGradAllReduce:
-    """all-reduce (average) the gradients of `params` with one NCCL call per step.
+    """all-reduce (average) the gradients of `params` over the data-parallel group, overlapped with backward.
 
     From the second step of a task on, the blocks carve every gradient buffer from one zero-filled fp32 arena per step
     (blocks._ZeroArena), in the same order on every rank, so the arena itself is the flat bucket and is reduced in
-    place.  Gradients that live elsewhere (the first step of a task, the few small heads that run on torch autograd)
-    go through a second, small flat buffer."""
+    place -- no flatten / unflatten copies.  The arena fills in backward order (heads first, language encoder last);
+    on CUDA the reduction is issued in `chunks` pieces on a communication stream while backward is still running:
+    after each block's backward a hook checks how far the arena has been carved and launches the NCCL all-reduce
+    (ReduceOp.AVG, so no separate scaling pass) of the finished prefix; only the last piece (the language-encoder and
+    embedding gradients, written last) is exposed after backward.  Parameters that receive a second gradient
+    contribution later in backward (the tied word-embedding / MLM-decoder matrix) keep both arena slices apart until
+    the reductions are done (the average of the sum is the sum of the averages), see blocks.PENDING_ADDS.
+    Gradients that live outside the arena (the first step of a task, the few small heads that run on torch autograd)
+    go through a second, small flat buffer.  Everything here is capturable in a CUDA graph (graphs.py)."""
 
-    def __init__(self, params, world_size=None):
+    def __init__(self, params, world_size=None, chunks=3):
         self.params = [p for p in params if p.requires_grad]
         self.world = world_size or (dist.get_world_size() if dist.is_initialized() else 1)
         self.buf = None
+        self.chunks = max(1, int(chunks))
+        self.comm = None
+        self._arena_id = None
+        self._done = 0
+        self._launched = 0
+        if self.world > 1:
+            from . import blocks
+            blocks.AFTER_BLOCK_BWD = self._after_block
+            blocks.DEFER_GRAD_ADDS = True
+
+    # ------------------------------------------------------------------ overlap with backward
+    def _overlap_ok(self, arena):
+        return arena is not None and arena.is_cuda and dist.get_backend() == "nccl"
+
+    def _reduce_range(self, arena, lo, hi):
+        if hi <= lo:
+            return
+        if self.comm is None:
+            self.comm = torch.cuda.Stream()
+        ev = torch.cuda.Event()
+        ev.record()
+        with torch.cuda.stream(self.comm):
+            self.comm.wait_event(ev)
+            dist.all_reduce(arena[lo:hi], op=dist.ReduceOp.AVG)
+
+    def _after_block(self):
+        """called by blocks._BlockFn.backward after every block (direct-gradient mode)"""
+        from . import blocks
+        A = blocks.ARENA
+        arena = A.buf
+        if self.world == 1 or not self._overlap_ok(arena):
+            return
+        if id(arena) != self._arena_id:                     # first block of a new step
+            self._arena_id, self._done, self._launched = id(arena), 0, 0
+        if self._launched >= self.chunks - 1:
+            return
+        step = arena.numel() // self.chunks
+        if A.off - self._done >= step:
+            self._reduce_range(arena, self._done, A.off)
+            self._done = A.off
+            self._launched += 1
 
     @torch.no_grad()
     def __call__(self):
         if self.world == 1:
             return
         from . import blocks
-        arena = blocks.ARENA.buf
+        A = blocks.ARENA
+        arena = A.buf
         grads = [p.grad for p in self.params if p.grad is not None]
         if not grads:
             return
         inv = 1.0 / self.world
-        if arena is not None and blocks.ARENA.off > 0:
+        if arena is not None and A.off > 0:
             if _CHECK_LAYOUT:      # debug (BEVBERT_CHECK_ARENA=1): every rank must have carved the same number of floats
-                n = torch.tensor([blocks.ARENA.off, -blocks.ARENA.off], dtype=torch.int64, device=arena.device)
+                n = torch.tensor([A.off, -A.off], dtype=torch.int64, device=arena.device)
                 dist.all_reduce(n, op=dist.ReduceOp.MAX)
                 if int(n[0]) != -int(n[1]):
                     raise RuntimeError("gradient arena layouts differ across ranks (%d..%d floats)" % (-int(n[1]), int(n[0])))
             base = arena.untyped_storage().data_ptr()
             rest = [g for g in grads if g.untyped_storage().data_ptr() != base]
-            used = arena[:blocks.ARENA.off]
-            used.mul_(inv)
-            dist.all_reduce(used)
+            if self._overlap_ok(arena):
+                if id(arena) != self._arena_id:
+                    self._arena_id, self._done, self._launched = id(arena), 0, 0
+                self._reduce_range(arena, self._done, A.off)          # the tail, written last by backward
+                self._done = A.off
+                torch.cuda.current_stream().wait_stream(self.comm)
+            else:
+                used = arena[:A.off]
+                used.mul_(inv)
+                dist.all_reduce(used)
         else:
             rest = grads
-        if not rest:
-            return
-        n = sum(g.numel() for g in rest)
-        if self.buf is None or self.buf.numel() < n:
-            self.buf = torch.empty(n, dtype=torch.float32, device=rest[0].device)
-        flat = self.buf[:n]
-        views = list(torch.split(flat, [g.numel() for g in rest]))
-        torch._foreach_copy_(views, [g.reshape(-1) for g in rest])
-        flat.mul_(inv)
-        dist.all_reduce(flat)
-        torch._foreach_copy_([g.view(-1) if g.is_contiguous() else g.reshape(-1) for g in rest], views)
+        pend = [g for _, g in blocks.PENDING_ADDS]
+        rest = rest + [g for g in pend if arena is None or g.untyped_storage().data_ptr() != arena.untyped_storage().data_ptr()]
+        if rest:
+            n = sum(g.numel() for g in rest)
+            if self.buf is None or self.buf.numel() < n:
+                self.buf = torch.empty(n, dtype=torch.float32, device=rest[0].device)
+            flat = self.buf[:n]
+            views = list(torch.split(flat, [g.numel() for g in rest]))
+            torch._foreach_copy_(views, [g.reshape(-1) for g in rest])
+            flat.mul_(inv)
+            dist.all_reduce(flat)
+            torch._foreach_copy_([g.view(-1) if g.is_contiguous() else g.reshape(-1) for g in rest], views)
+        blocks.apply_pending_adds()
 
 
 def broadcast_parameters(model, src=0):
@@ -80,3 +138,6 @@ def direct_param_grads(enable=True):
     not fire in this mode, so use it with FlatGradAllReduce or on a single GPU."""
     from . import blocks
     blocks.DIRECT_PARAM_GRADS = bool(enable)
+    if not enable:
+        blocks.DEFER_GRAD_ADDS = False
+        blocks.AFTER_BLOCK_BWD = None
