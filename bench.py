@@ -229,7 +229,9 @@ def run_ours(args, rank, world, local_rank):
         saved_fd = os.dup(1)
         os.dup2(2, 1)
         try:
-            dist.init_process_group("nccl", device_id=dev)
+            import datetime
+            dist.init_process_group("nccl", device_id=dev,
+                                    timeout=datetime.timedelta(seconds=int(os.environ.get("BEVBERT_NCCL_TIMEOUT_S", "600"))))
             dist.barrier()
             torch.cuda.synchronize()
         finally:
@@ -249,8 +251,10 @@ def run_ours(args, rank, world, local_rank):
             broadcast_parameters(model)
             reduce_grads = FlatGradAllReduce(model.parameters(), world)
     if not args.ddp:
-        from bevbert_b200.parallel import direct_param_grads
+        from bevbert_b200.parallel import direct_param_grads, enable_side_stream
         direct_param_grads(True)    # blocks assign p.grad themselves (no per-parameter AccumulateGrad nodes)
+        if args.side_stream:
+            enable_side_stream(True)    # weight-gradient GEMMs + bias column sums on a second stream
     if args.torch_optim:
         opt = torch.optim.AdamW(model.parameters(), lr=5e-5, weight_decay=0.01, fused=True)
     else:   # own multi-tensor AdamW + grad-norm clip kernel with the reference's update rule and hyper-parameters
@@ -271,9 +275,13 @@ def run_ours(args, rank, world, local_rank):
     wire = torch.bfloat16 if args.wire == "bf16" else None
     host_e2e = host if wire is None else {t: [prepare_batch(b, wire_dtype=wire) for b in bs] for t, bs in host.items()}
 
+    from bevbert_b200 import blocks as Bk
+
     def eager_step(batch, task):
         loss = net(batch, task).mean()
         loss.backward()
+        if reduce_grads is None:
+            Bk.join_side()           # side-stream mode: weight gradients landed (the reducer / optimizer also join)
         if reduce_grads is not None:
             reduce_grads()
         opt.step()
@@ -483,7 +491,7 @@ def run_ours(args, rank, world, local_rank):
                     "wire": "bf16 grid/view features, other inputs as collated" if wire is not None else "fp32 as collated",
                     "ms_per_step": ms_e2e / args.steps, "last_loss": losses[-1] if losses else None},
             "numa_node": numa, "gpu_launches": int(launches), "host_enqueue_ms_per_step": round(host_enqueue_ms, 3),
-            "step_mode": "cuda-graph replay per (task, static batch); sem/masksem eager" if graphed is not None else "eager launches",
+            "step_mode": "cuda-graph replay per (task, static batch)" if graphed is not None else "eager launches",
             "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
         }
         print(json.dumps(out))
@@ -502,6 +510,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--config", default="r2r", choices=sorted(WORKLOADS), help="workload: r2r = BASELINE configs[1] "
                     "(headline), rxr = configs[3], reverie = configs[4]")
+    ap.add_argument("--side-stream", type=int, default=1, help="1: weight-gradient GEMMs on a second stream (default)")
     ap.add_argument("--graphs", type=int, default=1, help="1: replay each (task, batch) step as one CUDA graph (default); 0: eager launches")
     ap.add_argument("--torch-optim", action="store_true", help="torch.optim.AdamW(fused=True) instead of bevbert_b200.optim.AdamW")
     ap.add_argument("--wire", choices=("bf16", "fp32"), default="bf16",

@@ -284,6 +284,14 @@ int bb_flash_bwd(const bb_flash_args* args, void* stream);
  * Weights are bf16 (out,in) row-major; self-attention uses the row-stacked Q|K|V weight (3Hd,Hd) in w_qkv,
  * cross-attention Wq in w_qkv and the stacked K|V weight (2Hd,Hd) in w_kv.
  * ------------------------------------------------------------------------------------------- */
+/* Optional: the backward executors (bb_attn_bwd / bb_ffn_bwd / bb_pano_bwd) launch their weight-gradient GEMMs and
+ * bias column sums on `side_stream` (forked from the caller's stream with an event each time) so that they overlap the
+ * dX chain.  The caller must (1) keep every buffer of a backward call (workspaces, dy, the forward workspace) alive
+ * until it has called bb_side_join(stream), which makes `stream` wait for the side stream, and (2) join before anything
+ * reads the parameter gradients.  NULL (default) = everything on the caller's stream. */
+int bb_set_side_stream(void* side_stream);
+int bb_side_join(void* stream);
+
 typedef struct bb_attn_desc {
   int32_t B, nq, nk, Hd, heads;
   int32_t cross;      /* 0: self-attention (c unused, nk == nq), 1: cross-attention over context c */

@@ -390,11 +390,23 @@ def set_precision(fp32):
     return False
 
 
+def set_side_stream(stream):
+    pass
+
+
+def side_stream():
+    return None
+
+
+def side_join():
+    pass
+
+
 def use_flash():
     return FLASH
 
 
-_NAMES = ["set_precision", "use_flash", "bev_cell_index", "set_attn_tc", "MtTable", "mt_cast_bf16", "mt_sumsq", "adamw_step", "flash_fwd", "flash_bwd", "attn_scores_fwd", "attn_scores_bwd", "gemm_profile", "gemm_profile_records", "native_sublayers", "attn_desc", "ffn_desc", "pano_desc", "sublayer_ws_bytes", "sublayer_fwd", "sublayer_bwd", "gemm", "act_dtype", "drop_params", "launch_count", "reset_launch_count", "bev_lift_index",
+_NAMES = ["set_side_stream", "side_stream", "side_join", "set_precision", "use_flash", "bev_cell_index", "set_attn_tc", "MtTable", "mt_cast_bf16", "mt_sumsq", "adamw_step", "flash_fwd", "flash_bwd", "attn_scores_fwd", "attn_scores_bwd", "gemm_profile", "gemm_profile_records", "native_sublayers", "attn_desc", "ffn_desc", "pano_desc", "sublayer_ws_bytes", "sublayer_fwd", "sublayer_bwd", "gemm", "act_dtype", "drop_params", "launch_count", "reset_launch_count", "bev_lift_index",
           "bev_scatter_mean", "bev_scatter_sem", "cast_to_act", "cast_to_f32", "dropout_act", "layernorm_fwd",
           "layernorm_bwd", "colsum", "softmax_fwd", "softmax_bwd", "embed_sum", "embed_scatter_grad", "gather_rows",
           "scatter_add_rows", "gelu_bwd", "relu_bwd", "add_rows", "scale_rows_", "segment_wsum", "segment_wsum_bwd",

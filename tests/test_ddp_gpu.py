@@ -28,7 +28,9 @@ def _worker(rank, world, port, task, ret):
     from bevbert_b200.optim import AdamW, build_param_groups
     from bevbert_b200.parallel import FlatGradAllReduce, broadcast_parameters, direct_param_grads
     from helpers import small_config, small_synth
-    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    import datetime
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank),
+                            timeout=datetime.timedelta(seconds=90))
     cfg = small_config()
     full = synth.make_batch(small_synth(batch_size=4), seed=9, task=task)
     shard = synth.batch_to(prepare_batch(synth.split_batch(full, world)[rank]), "cuda")

@@ -37,7 +37,7 @@ def _run(seq, b, lr, graphed):
     if graphed:
         step = GraphedTrainStep(m, o, warmup=1)
         losses = [float(step(b[t], t)) for t in seq]
-        assert step.launches(b["mlm"], "mlm") and step.launches(b["sap"], "sap") and step.launches(b["masksem"], "masksem") is None
+        assert step.launches(b["mlm"], "mlm") and step.launches(b["sap"], "sap")
     else:
         for t in seq:
             loss = m(b[t], t).mean()
@@ -88,3 +88,53 @@ def test_graph_replay_draws_fresh_dropout_masks():
         assert len(set(round(x, 6) for x in losses[2:])) >= 3, losses   # replays 3..6 use different masks
     finally:
         direct_param_grads(False)
+
+
+def test_masksem_sync_free_mean_equals_per_item_mean():
+    """masksem in the graph-capturable mode (mean over all cells weighted by the device-side selection) gives the value
+    and the gradients of `forward(...).mean()` on the reference's variable-length per-item loss."""
+    b = _batches()
+    m, _ = _setup()
+    l1 = m(b["masksem"], "masksem").mean()
+    l1.backward()
+    g1 = {n: p.grad.clone() for n, p in m.named_parameters() if p.grad is not None}
+    m.zero_grad(set_to_none=True)
+    m.sync_free_mean = True
+    l2 = m(b["masksem"], "masksem")
+    m.sync_free_mean = False
+    assert l2.dim() == 0 and abs(float(l1) - float(l2)) <= 1e-4 * abs(float(l1))
+    l2.backward()
+    num = sum(float((p.grad - g1[n]).norm()) ** 2 for n, p in m.named_parameters() if p.grad is not None)
+    den = sum(float(g.norm()) ** 2 for g in g1.values())
+    assert (num / den) ** 0.5 < 2e-2, (num / den) ** 0.5        # two bf16 runs with different row sets in the head GEMMs
+
+
+def test_side_stream_weight_gradients_match_single_stream():
+    """parallel.enable_side_stream: weight-gradient GEMMs / bias column sums on a second stream (fork per call, one join
+    after backward, buffers kept alive, second contributions deferred) give the single-stream gradients."""
+    from bevbert_b200 import blocks
+    from bevbert_b200.parallel import enable_side_stream
+    b = _batches()
+    grads = {}
+    for side in (False, True):
+        m, _ = _setup()
+        direct_param_grads(True)
+        if side:
+            enable_side_stream(True)
+        try:
+            for t in ("mlm", "sap"):
+                m.zero_grad(set_to_none=True)
+                m(b[t], t).mean().backward()
+                blocks.join_side()
+                torch.cuda.synchronize()
+                grads[(side, t)] = {n: p.grad.clone() for n, p in m.named_parameters() if p.grad is not None}
+        finally:
+            if side:
+                enable_side_stream(False)
+            direct_param_grads(False)
+    for t in ("mlm", "sap"):
+        a, c = grads[(False, t)], grads[(True, t)]
+        assert set(a) == set(c)
+        num = sum(float((c[n] - a[n]).norm()) ** 2 for n in a)
+        den = sum(float(a[n].norm()) ** 2 for n in a)
+        assert (num / den) ** 0.5 < 1e-3, (t, (num / den) ** 0.5)

@@ -142,6 +142,8 @@ _SIGNATURES = {
     "bb_set_attn_tc": (c_int, [c_int]),
     "bb_attn_tc_trace": (c_int, [c_void_p]),
     "bb_flash_bwd": (c_int, [C.POINTER(FlashArgs), c_void_p]),
+    "bb_set_side_stream": (c_int, [c_void_p]),
+    "bb_side_join": (c_int, [c_void_p]),
     "bb_attn_ws_bytes": (c_int, [C.POINTER(AttnDesc), C.POINTER(c_i64), C.POINTER(c_i64)]),
     "bb_attn_fwd": (c_int, [C.POINTER(AttnDesc), c_void_p]),
     "bb_attn_bwd": (c_int, [C.POINTER(AttnDesc), c_void_p]),

@@ -216,11 +216,13 @@ class _ZeroArena:
         self.need = 0
         self.tag = None
         self.est = {}
+        self.step_id = 0        # incremented per step: identifies the current arena (id() of a freed tensor is reused)
 
     def new_step(self, tag=None):
         if self.need:
             self.est[self.tag] = self.need
         self.buf, self.off, self.need, self.tag = None, 0, 0, tag
+        self.step_id += 1
 
     def take(self, device, n):
         n4 = (n + 3) // 4 * 4                       # keep every slice 16-byte aligned
@@ -535,6 +537,7 @@ def attn_native_bwd(st, dy, want_dbias=False):
     if want_dbias:
         z = z + [zeros_f32(dev, B, nq, nk, scratch=True)]      # activation gradient: its size depends on the batch
     gws = _ws(st["a_bwd"], dev)
+    st["a_gws"] = (gws, dy)      # side-stream mode: read by kernels that may still be in flight after this call returns
     dx = torch.empty(B * nq, Hd, dtype=K.act_dtype(), device=dev)
     dc = torch.empty(B * nk, Hd, dtype=K.act_dtype(), device=dev) if cross else None
     d.dy, d.gws, d.dx = dy.data_ptr(), gws.data_ptr(), dx.data_ptr()
@@ -585,6 +588,7 @@ def ffn_native_bwd(st, dy):
         dy = dy.contiguous()
     dg, db, dW2, db2, dW1, db1 = ZeroPool(dev, (Hd,), (Hd,), (Hd, Fd), (Hd,), (Fd, Hd), (Fd,)).out
     gws = _ws(st["f_bwd"], dev)
+    st["f_gws"] = (gws, dy)
     da = torch.empty(M, Hd, dtype=K.act_dtype(), device=dev)
     d.dy, d.gws, d.da = dy.data_ptr(), gws.data_ptr(), da.data_ptr()
     d.dgamma, d.dbeta, d.dw2, d.db2, d.dw1, d.db1 = (dg.data_ptr(), db.data_ptr(), dW2.data_ptr(), db2.data_ptr(),
@@ -694,6 +698,7 @@ class PanoLayerImpl:
         z = ZeroPool(dev, (3 * Hd, Hd), (3 * Hd,), (Hd, Hd), (Hd,), (Fd, Hd), (Fd,), (Hd, Fd), (Hd,), (Hd,), (Hd,), (Hd,),
                      (Hd,)).out
         gws = _ws(st["p_bwd"], dev)
+        st["p_gws"] = (gws, dy)
         dx = torch.empty(N * V, Hd, dtype=K.act_dtype(), device=dev)
         d.dy, d.gws, d.dx = dy.data_ptr(), gws.data_ptr(), dx.data_ptr()
         (d.dw_in, d.db_in, d.dw_out, d.db_out, d.dw1, d.db1, d.dw2, d.db2, d.dg1, d.dbe1, d.dg2, d.dbe2) = \
@@ -1078,10 +1083,28 @@ DEFER_GRAD_ADDS = False      # a second contribution to a parameter waits in PEN
 PENDING_ADDS = []
 
 
+SIDE_KEEP = []               # side-stream mode: everything a backward call's side-stream kernels read, kept until the join
+
+
 def apply_pending_adds():
     for p, g in PENDING_ADDS:
         p.grad.add_(g)
     PENDING_ADDS.clear()
+
+
+def side_active():
+    return K.side_stream() is not None
+
+
+def join_side():
+    """End of backward in side-stream mode (parallel.enable_side_stream): the current stream waits for the weight-gradient
+    kernels, the buffers they read are released, second gradient contributions are added."""
+    if K.side_stream() is None:
+        return
+    K.side_join()
+    SIDE_KEEP.clear()
+    if AFTER_BLOCK_BWD is None:          # with an overlapped reducer, the reducer applies them after its all-reduces
+        apply_pending_adds()
 
 
 
@@ -1099,6 +1122,8 @@ class _BlockFn(torch.autograd.Function):
     def backward(ctx, *gouts):
         with torch.no_grad():
             gin, gpar = ctx.impl.bwd(ctx.st, gouts, ctx.params)
+        if side_active():
+            SIDE_KEEP.append((ctx.st, gouts))
         ctx.st = None
         gin = list(gin) + [None] * (ctx.n_in - len(gin))
         needs = ctx.needs_input_grad[2:]
@@ -1111,7 +1136,7 @@ class _BlockFn(torch.autograd.Function):
                         g = g.contiguous()
                     if p.grad is None:
                         p.grad = g
-                    elif DEFER_GRAD_ADDS:
+                    elif DEFER_GRAD_ADDS or side_active():
                         PENDING_ADDS.append((p, g))
                     else:
                         p.grad.add_(g)

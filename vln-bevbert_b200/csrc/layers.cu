@@ -85,6 +85,25 @@ static AttnLayout attn_layout(const bb_attn_desc* d) {
 
 static inline char* at(void* base, int64_t off) { return reinterpret_cast<char*>(base) + off; }
 
+// Optional side stream for the weight-gradient products (dW = dY^T X, split-K fp32 atomics) and the bias column sums:
+// nothing in backward depends on them, they are small (0.4-1.6 waves of tiles on the 2560-row language-encoder
+// layers) and so overlap well with the dX chain on the main stream.  side_for() forks: the side stream waits for
+// everything enqueued on `main` so far; the caller joins once after backward (bb_side_join) and keeps the buffers those
+// kernels read alive until then.  Inside a CUDA-graph capture this becomes a fork / join of the graph.
+static cudaStream_t g_side = nullptr;
+static cudaEvent_t g_fork_ev[32];
+static int g_fork_i = 0;
+static bool g_side_used = false;
+static void* side_for(void* main_stream) {
+  if (!g_side) return main_stream;
+  cudaEvent_t& ev = g_fork_ev[g_fork_i++ & 31];
+  if (!ev) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+  cudaEventRecord(ev, (cudaStream_t)main_stream);
+  cudaStreamWaitEvent(g_side, ev, 0);
+  g_side_used = true;
+  return g_side;
+}
+
 // y = epi(x W^T + b)
 static int lin_fwd(const void* x, const void* w, void* out, int64_t M, int N, int K, const float* bias, int act,
                    void* pre, uint64_t seed, uint32_t th, float sc, const void* add_in, int out_f32, void* stream) {
@@ -283,7 +302,7 @@ extern "C" int bb_attn_bwd(const bb_attn_desc* d, void* stream) {
   TRY(bb_layernorm_bwd(d->dy, 0, at(d->ws, L.ao), 0, d->x, d->gamma, reinterpret_cast<const float*>(at(d->ws, L.mean)),
                        reinterpret_cast<const float*>(at(d->ws, L.rstd)), Mq, Hd, d->seed_h, d->th_h, d->sc_h, 0, 0, 1.0f,
                        dao, 0, dres, d->dgamma, d->dbeta, d->db_o, stream));
-  TRY(lin_bwd_dw(dao, at(d->ws, L.ctx), d->dw_o, Mq, Hd, Hd, stream));
+  TRY(lin_bwd_dw(dao, at(d->ws, L.ctx), d->dw_o, Mq, Hd, Hd, side_for(stream)));
   TRY(lin_bwd_dx(dao, d->w_o, at(d->gws, L.dctx), Mq, Hd, Hd, 0, nullptr, nullptr, stream));
   if (!d->cross) {
     char* qkv = at(d->ws, L.qkv);
@@ -291,8 +310,8 @@ extern "C" int bb_attn_bwd(const bb_attn_desc* d, void* stream) {
     const int Lq = 3 * Hd;
     TRY(attn_core_bwd(d, L, qkv, Lq, qkv + (int64_t)Hd * 2, Lq, qkv + (int64_t)2 * Hd * 2, Lq, dqkv, Lq,
                       dqkv + (int64_t)Hd * 2, Lq, dqkv + (int64_t)2 * Hd * 2, Lq, stream));
-    TRY(lin_bwd_dw(dqkv, d->x, d->dw_qkv, Mq, 3 * Hd, Hd, stream));
-    TRY(bb_colsum_bf16(dqkv, Mq, 3 * Hd, 3 * Hd, d->db_qkv, stream));
+    TRY(lin_bwd_dw(dqkv, d->x, d->dw_qkv, Mq, 3 * Hd, Hd, side_for(stream)));
+    TRY(bb_colsum_bf16(dqkv, Mq, 3 * Hd, 3 * Hd, d->db_qkv, side_for(stream)));
     return lin_bwd_dx(dqkv, d->w_qkv, d->dx, Mq, 3 * Hd, Hd, 0, nullptr, dres, stream);
   }
   if (!d->dc) return set_error("bb_attn_bwd: cross attention needs dc");
@@ -302,11 +321,11 @@ extern "C" int bb_attn_bwd(const bb_attn_desc* d, void* stream) {
   char* dkv = at(d->gws, L.dkv);
   TRY(attn_core_bwd(d, L, q, Hd, kv, 2 * Hd, kv + (int64_t)Hd * 2, 2 * Hd, dq, Hd, dkv, 2 * Hd, dkv + (int64_t)Hd * 2,
                     2 * Hd, stream));
-  TRY(lin_bwd_dw(dq, d->x, d->dw_qkv, Mq, Hd, Hd, stream));
-  TRY(bb_colsum_bf16(dq, Mq, Hd, Hd, d->db_qkv, stream));
+  TRY(lin_bwd_dw(dq, d->x, d->dw_qkv, Mq, Hd, Hd, side_for(stream)));
+  TRY(bb_colsum_bf16(dq, Mq, Hd, Hd, d->db_qkv, side_for(stream)));
   TRY(lin_bwd_dx(dq, d->w_qkv, d->dx, Mq, Hd, Hd, 0, nullptr, dres, stream));
-  TRY(lin_bwd_dw(dkv, d->c, d->dw_kv, Mk, 2 * Hd, Hd, stream));
-  TRY(bb_colsum_bf16(dkv, Mk, 2 * Hd, 2 * Hd, d->db_kv, stream));
+  TRY(lin_bwd_dw(dkv, d->c, d->dw_kv, Mk, 2 * Hd, Hd, side_for(stream)));
+  TRY(bb_colsum_bf16(dkv, Mk, 2 * Hd, 2 * Hd, d->db_kv, side_for(stream)));
   return lin_bwd_dx(dkv, d->w_kv, d->dc, Mk, 2 * Hd, Hd, 0, nullptr, nullptr, stream);
 }
 
@@ -360,10 +379,10 @@ extern "C" int bb_ffn_bwd(const bb_ffn_desc* d, void* stream) {
   TRY(bb_layernorm_bwd(d->dy, 0, at(d->ws, L.fo), 0, d->a, d->gamma, reinterpret_cast<const float*>(at(d->ws, L.mean)),
                        reinterpret_cast<const float*>(at(d->ws, L.rstd)), d->M, d->Hd, d->seed_h, d->th_h, d->sc_h, 0, 0,
                        1.0f, dfo, 0, dres, d->dgamma, d->dbeta, d->db2, stream));
-  TRY(lin_bwd_dw(dfo, at(d->ws, L.h), d->dw2, d->M, d->Hd, d->Fd, stream));
+  TRY(lin_bwd_dw(dfo, at(d->ws, L.h), d->dw2, d->M, d->Hd, d->Fd, side_for(stream)));
   TRY(lin_bwd_dx(dfo, d->w2, dhpre, d->M, d->Hd, d->Fd, 1, at(d->ws, L.hpre), nullptr, stream));
-  TRY(lin_bwd_dw(dhpre, d->a, d->dw1, d->M, d->Fd, d->Hd, stream));
-  TRY(bb_colsum_bf16(dhpre, d->M, d->Fd, d->Fd, d->db1, stream));
+  TRY(lin_bwd_dw(dhpre, d->a, d->dw1, d->M, d->Fd, d->Hd, side_for(stream)));
+  TRY(bb_colsum_bf16(dhpre, d->M, d->Fd, d->Fd, d->db1, side_for(stream)));
   return lin_bwd_dx(dhpre, d->w1, d->da, d->M, d->Fd, d->Hd, 0, nullptr, dres, stream);
 }
 
@@ -478,12 +497,12 @@ extern "C" int bb_pano_bwd(const bb_pano_desc* d, void* stream) {
     TRY(bb_dropout_bf16(d->dy, at(d->gws, L.dy3), M * Hd, d->seed3, d->th_h, d->sc_h, stream));
     dy3 = at(d->gws, L.dy3);
   }
-  TRY(lin_bwd_dw(dy3, at(d->ws, L.f), d->dw2, M, Hd, Fd, stream));
-  TRY(bb_colsum_bf16(dy3, M, Hd, Hd, d->db2, stream));
+  TRY(lin_bwd_dw(dy3, at(d->ws, L.f), d->dw2, M, Hd, Fd, side_for(stream)));
+  TRY(bb_colsum_bf16(dy3, M, Hd, Hd, d->db2, side_for(stream)));
   TRY(lin_bwd_dx(dy3, d->w2, at(d->gws, L.dfpre), M, Hd, Fd, 1, at(d->ws, L.fpre), nullptr, stream, d->seed2, d->th_h,
                  d->sc_h));
-  TRY(lin_bwd_dw(at(d->gws, L.dfpre), at(d->ws, L.h2), d->dw1, M, Fd, Hd, stream));
-  TRY(bb_colsum_bf16(at(d->gws, L.dfpre), M, Fd, Fd, d->db1, stream));
+  TRY(lin_bwd_dw(at(d->gws, L.dfpre), at(d->ws, L.h2), d->dw1, M, Fd, Hd, side_for(stream)));
+  TRY(bb_colsum_bf16(at(d->gws, L.dfpre), M, Fd, Fd, d->db1, side_for(stream)));
   TRY(lin_bwd_dx(at(d->gws, L.dfpre), d->w1, at(d->gws, L.dh2), M, Fd, Hd, 0, nullptr, nullptr, stream));
   TRY(bb_layernorm_bwd(at(d->gws, L.dh2), 0, at(d->ws, L.x1), 0, nullptr, d->g2,
                        reinterpret_cast<const float*>(at(d->ws, L.m2)), reinterpret_cast<const float*>(at(d->ws, L.r2)), M,
@@ -495,19 +514,34 @@ extern "C" int bb_pano_bwd(const bb_pano_desc* d, void* stream) {
     TRY(bb_dropout_bf16(at(d->gws, L.dx1), at(d->gws, L.d1g), M * Hd, d->seed1, d->th_h, d->sc_h, stream));
     d1g = at(d->gws, L.d1g);
   }
-  TRY(lin_bwd_dw(d1g, at(d->ws, L.A.ctx), d->dw_out, M, Hd, Hd, stream));
-  TRY(bb_colsum_bf16(d1g, M, Hd, Hd, d->db_out, stream));
+  TRY(lin_bwd_dw(d1g, at(d->ws, L.A.ctx), d->dw_out, M, Hd, Hd, side_for(stream)));
+  TRY(bb_colsum_bf16(d1g, M, Hd, Hd, d->db_out, side_for(stream)));
   TRY(lin_bwd_dx(d1g, d->w_out, at(d->gws, L.A.dctx), M, Hd, Hd, 0, nullptr, nullptr, stream));
   char* qkv = at(d->ws, L.qkv);
   char* dqkv = at(d->gws, L.dqkv);
   const int Lq = 3 * Hd;
   TRY(attn_core_bwd(&a, L.A, qkv, Lq, qkv + (int64_t)Hd * 2, Lq, qkv + (int64_t)2 * Hd * 2, Lq, dqkv, Lq,
                     dqkv + (int64_t)Hd * 2, Lq, dqkv + (int64_t)2 * Hd * 2, Lq, stream));
-  TRY(lin_bwd_dw(dqkv, at(d->ws, L.h1), d->dw_in, M, 3 * Hd, Hd, stream));
-  TRY(bb_colsum_bf16(dqkv, M, 3 * Hd, 3 * Hd, d->db_in, stream));
+  TRY(lin_bwd_dw(dqkv, at(d->ws, L.h1), d->dw_in, M, 3 * Hd, Hd, side_for(stream)));
+  TRY(bb_colsum_bf16(dqkv, M, 3 * Hd, 3 * Hd, d->db_in, side_for(stream)));
   TRY(lin_bwd_dx(dqkv, d->w_in, at(d->gws, L.dh1), M, 3 * Hd, Hd, 0, nullptr, nullptr, stream));
   TRY(bb_layernorm_bwd(at(d->gws, L.dh1), 0, d->x, 0, nullptr, d->g1, reinterpret_cast<const float*>(at(d->ws, L.m1)),
                        reinterpret_cast<const float*>(at(d->ws, L.r1)), M, Hd, 0, 0, 1.0f, 0, 0, 1.0f, at(d->gws, L.dxln), 0,
                        nullptr, d->dg1, d->dbe1, nullptr, stream));
   return bb_add_bf16(at(d->gws, L.dxln), at(d->gws, L.dx1), d->dx, M * Hd, stream);
+}
+
+extern "C" int bb_set_side_stream(void* side_stream) {
+  bb::g_side = (cudaStream_t)side_stream;
+  return 0;
+}
+extern "C" int bb_side_join(void* main_stream) {
+  using namespace bb;
+  if (!g_side || !g_side_used) return 0;
+  static cudaEvent_t ev = nullptr;
+  if (!ev) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+  if (cudaEventRecord(ev, g_side) != cudaSuccess || cudaStreamWaitEvent((cudaStream_t)main_stream, ev, 0) != cudaSuccess)
+    return set_error("bb_side_join: event record / wait failed");
+  g_side_used = false;
+  return 0;
 }

@@ -12,8 +12,9 @@ What makes a step replayable here:
   * the optimizer's host half (per-parameter step counters, bias-corrected step sizes, lr schedule) is redone before
     each replay by `optim.AdamW.advance`; the graph re-uploads the pinned launch table and runs the update kernels;
   * parameter gradients are carved from the per-step arena inside the graph's memory pool: same addresses every replay.
-A graph is keyed by (task, identity and shapes of the batch tensors).  Tasks whose forward needs a device->host
-synchronisation (sem / masksem: the number of labelled cells is computed on the device) run eagerly.
+A graph is keyed by (task, identity and shapes of the batch tensors).  sem / masksem, whose per-item loss has a
+device-computed length, run in the model's `sync_free_mean` mode (mean over a device-side weight, same value and
+gradients); a step whose capture fails (a host synchronisation somewhere in forward) falls back to eager launches.
 """
 import torch
 
@@ -21,7 +22,7 @@ from . import blocks
 from . import kernels as K
 from . import _lib
 
-EAGER_TASKS = ("sem", "masksem")
+EAGER_TASKS = ()      # every pre-training task is capturable (sem / masksem through the model's sync_free_mean mode)
 
 
 class GraphedTrainStep:
@@ -42,8 +43,18 @@ class GraphedTrainStep:
         return (task, id(batch)) + tuple((k, v.data_ptr(), tuple(v.shape)) for k, v in sorted(batch.items())
                                          if torch.is_tensor(v))
 
+    def _forward(self, batch, task):
+        mod = self.net.module if hasattr(self.net, "module") else self.net
+        if task.startswith(("sem", "masksem")) and hasattr(mod, "sync_free_mean"):
+            mod.sync_free_mean = True
+            try:
+                return self.net(batch, task)
+            finally:
+                mod.sync_free_mean = False
+        return self.net(batch, task)
+
     def _eager(self, batch, task):
-        loss = self.loss_fn(self.net(batch, task))
+        loss = self.loss_fn(self._forward(batch, task))
         loss.backward()
         if self.reduce_grads is not None:
             self.reduce_grads()
@@ -55,7 +66,7 @@ class GraphedTrainStep:
         self.salt_host[0] = blocks._mix64(self.nstep * 0x9E3779B97F4A7C15 + 12345) & 0x7FFFFFFFFFFFFFFF
 
     def __call__(self, batch, task):
-        if task.startswith(EAGER_TASKS):
+        if EAGER_TASKS and task.startswith(EAGER_TASKS):
             self._next_salt()
             self.salt_dev.copy_(self.salt_host, non_blocking=True)
             return self._eager(batch, task)
@@ -72,6 +83,14 @@ class GraphedTrainStep:
             self._next_salt()
             self.salt_dev.copy_(self.salt_host, non_blocking=True)
             return self._eager(batch, task)
+        if ent["graph"] is not None and self.reduce_grads is not None:
+            # data-parallel: the graph holds forward + backward; the NCCL all-reduce and the optimizer run eagerly on the
+            # gradients the graph left in its (static) arena -- collectives stay out of the capture (a rank whose capture
+            # failed would otherwise execute them while the others only record them)
+            self._next_salt()
+            ent["graph"].replay()
+            self._after_backward_eager(ent)
+            return ent["loss"]
         if ent["graph"] is None:
             try:
                 self._capture(ent, batch, task)
@@ -92,6 +111,17 @@ class GraphedTrainStep:
             ent["graph"].replay()
         return ent["loss"]
 
+    def _after_backward_eager(self, ent):
+        """data-parallel replay: hand the graph's gradient tensors back to the parameters, then all-reduce + step"""
+        A = blocks.ARENA
+        A.buf, A.off, A.need, A.tag = ent["arena"]
+        A.step_id += 1
+        for p, g in ent["grads"]:
+            p.grad = g
+        blocks.PENDING_ADDS[:] = ent["pending"]
+        self.reduce_grads()
+        self.opt.step()
+
     def _capture(self, ent, batch, task):
         for p in self.net.parameters():
             p.grad = None
@@ -101,18 +131,34 @@ class GraphedTrainStep:
         g = torch.cuda.CUDAGraph()
         self._next_salt()
         n0 = K.launch_count()
-        with torch.cuda.graph(g, pool=self.pool):
-            self.salt_dev.copy_(self.salt_host, non_blocking=True)
-            loss = self.loss_fn(self.net(batch, task))
-            loss.backward()
-            if self.reduce_grads is not None:
-                self.reduce_grads()
-            self.opt.step()
-            ent["loss"] = loss.detach()
+        dp = self.reduce_grads is not None
+        hook, blocks.AFTER_BLOCK_BWD = blocks.AFTER_BLOCK_BWD, (None if dp else blocks.AFTER_BLOCK_BWD)
+        try:
+            with torch.cuda.graph(g, pool=self.pool):
+                self.salt_dev.copy_(self.salt_host, non_blocking=True)
+                loss = self.loss_fn(self._forward(batch, task))
+                loss.backward()
+                if dp:
+                    blocks.join_side()       # side-stream work rejoins inside the graph; gradients stay in the arena
+                else:
+                    self.opt.step()
+                ent["loss"] = loss.detach()
+        finally:
+            blocks.AFTER_BLOCK_BWD = hook
         ent["launches"] = K.launch_count() - n0
-        ent["graph"], ent["sig"] = g, self.opt.last_sig
-        # the capture only RECORDED the step (and advanced the optimizer's host counters for it): run it once
-        g.replay()
+        ent["graph"] = g
+        if dp:
+            params = [p for p in self.net.parameters() if p.grad is not None]
+            ent["grads"] = [(p, p.grad) for p in params]
+            ent["pending"] = list(blocks.PENDING_ADDS)
+            A = blocks.ARENA
+            ent["arena"] = (A.buf, A.off, A.need, A.tag)
+            g.replay()                       # the capture only RECORDED forward + backward: run them once
+            self._after_backward_eager(ent)
+        else:
+            ent["sig"] = self.opt.last_sig
+            # the capture only RECORDED the step (and advanced the optimizer's host counters for it): run it once
+            g.replay()
 
     def launches(self, batch, task):
         """kernels of libbevbert_b200.so inside the captured step of (batch, task), or None when it runs eagerly."""

@@ -150,6 +150,26 @@ def native_sublayers():
     return not _FP32_ARM
 
 
+_SIDE = None
+
+
+def set_side_stream(stream):
+    """torch.cuda.Stream (or None) for the weight-gradient GEMMs of the native backward executors (bb_set_side_stream)."""
+    global _SIDE
+    _SIDE = stream
+    _lib.check(_lib.load().bb_set_side_stream(stream.cuda_stream if stream is not None else None), "bb_set_side_stream")
+
+
+def side_stream():
+    return _SIDE
+
+
+def side_join():
+    """the current stream waits for the side stream (no-op when nothing was forked since the last join)"""
+    if _SIDE is not None:
+        _lib.check(_lib.load().bb_side_join(_stream()), "bb_side_join")
+
+
 def attn_desc():
     return _lib.AttnDesc()
 

@@ -242,8 +242,20 @@ class GlocalTextPathCMTPreTraining(PreTrainedBase):
         obj_logits = obj_logits.masked_fill(obj_masks.logical_not(), -float("inf"))
         return F.cross_entropy(obj_logits, obj_labels, reduction="none") if compute_loss else obj_logits
 
+    # sync_free_mean = True (set by graphs.GraphedTrainStep): sem / masksem return the MEAN of the per-item loss as a
+    # 0-d tensor, computed over all cells with the selection as a weight -- the number of labelled cells is known only
+    # on the device (lift_splat computes bev_sem_masks there), so the reference's variable-length (n_cells, 40) result
+    # would need a device->host synchronisation and could not live in a CUDA graph.  Same value and gradients as
+    # `forward(...).mean()`.
+    sync_free_mean = False
+
     def _sem(self, args, bev_sems, sel, compute_loss):
         bev_embeds = self.bert.forward_sem(*args, sem_pred_token=self.sem_pred_token)
+        if self.sync_free_mean and compute_loss:
+            logits = self.local_sem_head(self.rt, bev_embeds.reshape(-1, bev_embeds.shape[-1]))
+            per = F.binary_cross_entropy_with_logits(logits, bev_sems.reshape(-1, bev_sems.shape[-1]).float(), reduction="none")
+            w = sel.reshape(-1, 1).to(per.dtype)
+            return (per * w).sum() / (w.sum() * per.shape[1])
         sem_logits = self.local_sem_head(self.rt, self._masked_rows(bev_embeds, sel))
         sem_labels = bev_sems[sel].float()
         if not compute_loss:

@@ -148,6 +148,8 @@ class AdamW:
 
     @torch.no_grad()
     def step(self, grad_scale=1.0, set_to_none=True):
+        from . import blocks
+        blocks.join_side()      # side-stream mode: weight gradients must have landed (no-op otherwise)
         sig = tuple(i for i, (_, p) in enumerate(self.flat) if p.grad is not None)
         if not sig:
             return None

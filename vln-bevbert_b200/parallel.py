@@ -56,8 +56,12 @@ class FlatGradAllReduce:
             self.comm = torch.cuda.Stream()
         ev = torch.cuda.Event()
         ev.record()
+        from . import kernels as K
+        side = K.side_stream()
         with torch.cuda.stream(self.comm):
             self.comm.wait_event(ev)
+            if side is not None:            # weight gradients of the finished prefix may still be on the side stream
+                self.comm.wait_stream(side)
             dist.all_reduce(arena[lo:hi], op=dist.ReduceOp.AVG)
 
     def _after_block(self):
@@ -67,8 +71,8 @@ class FlatGradAllReduce:
         arena = A.buf
         if self.world == 1 or not self._overlap_ok(arena):
             return
-        if id(arena) != self._arena_id:                     # first block of a new step
-            self._arena_id, self._done, self._launched = id(arena), 0, 0
+        if A.step_id != self._arena_id:                     # first block of a new step
+            self._arena_id, self._done, self._launched = A.step_id, 0, 0
         if self._launched >= self.chunks - 1:
             return
         step = arena.numel() // self.chunks
@@ -79,9 +83,14 @@ class FlatGradAllReduce:
 
     @torch.no_grad()
     def __call__(self):
-        if self.world == 1:
-            return
         from . import blocks
+        if blocks.side_active():
+            from . import kernels as K
+            K.side_join()
+            blocks.SIDE_KEEP.clear()
+        if self.world == 1:
+            blocks.apply_pending_adds()
+            return
         A = blocks.ARENA
         arena = A.buf
         grads = [p.grad for p in self.params if p.grad is not None]
@@ -97,8 +106,8 @@ class FlatGradAllReduce:
             base = arena.untyped_storage().data_ptr()
             rest = [g for g in grads if g.untyped_storage().data_ptr() != base]
             if self._overlap_ok(arena):
-                if id(arena) != self._arena_id:
-                    self._arena_id, self._done, self._launched = id(arena), 0, 0
+                if A.step_id != self._arena_id:
+                    self._arena_id, self._done, self._launched = A.step_id, 0, 0
                 self._reduce_range(arena, self._done, A.off)          # the tail, written last by backward
                 self._done = A.off
                 torch.cuda.current_stream().wait_stream(self.comm)
@@ -129,6 +138,23 @@ def broadcast_parameters(model, src=0):
         return
     for t in list(model.parameters()) + list(model.buffers()):
         dist.broadcast(t.data, src)
+
+
+def enable_side_stream(enable=True):
+    """Run the weight-gradient GEMMs and bias column sums of the native backward executors on a second CUDA stream
+    (kernels.set_side_stream): nothing in backward depends on them, and the 2560-row language-encoder layers fill only
+    0.4-1.6 waves of GEMM tiles, so they overlap the dX chain.  Requires direct parameter gradients and an end-of-backward
+    join: `bevbert_b200.optim.AdamW.step`, `FlatGradAllReduce.__call__` and `graphs.GraphedTrainStep` call
+    `blocks.join_side()` themselves; a hand-written loop calls it after `loss.backward()`."""
+    from . import kernels as K
+    if enable:
+        direct_param_grads(True)
+        if K.side_stream() is None:
+            K.set_side_stream(torch.cuda.Stream())
+    else:
+        from . import blocks
+        blocks.join_side()
+        K.set_side_stream(None)
 
 
 def direct_param_grads(enable=True):
