@@ -25,6 +25,19 @@ from . import _lib
 EAGER_TASKS = ()      # every pre-training task is capturable (sem / masksem through the model's sync_free_mean mode)
 
 
+_SALT = {}      # device -> (pinned host word, device word): registered with the library once and never freed
+
+
+def _salt_buffers(dev):
+    key = (dev.type, dev.index)
+    if key not in _SALT:
+        host = torch.zeros(1, dtype=torch.int64).pin_memory()
+        word = torch.zeros(1, dtype=torch.int64, device=dev)
+        _lib.check(_lib.load().bb_set_drop_salt_ptr(word.data_ptr()), "bb_set_drop_salt_ptr")
+        _SALT[key] = (host, word)
+    return _SALT[key]
+
+
 class GraphedTrainStep:
     def __init__(self, net, optimizer, reduce_grads=None, warmup=2, loss_fn=None):
         self.net, self.opt, self.reduce_grads, self.warmup = net, optimizer, reduce_grads, warmup
@@ -32,8 +45,7 @@ class GraphedTrainStep:
         self.entries = {}
         self.pool = None
         dev = next(net.parameters()).device
-        self.salt_host = torch.zeros(1, dtype=torch.int64).pin_memory()
-        self.salt_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.salt_host, self.salt_dev = _salt_buffers(dev)
         _lib.check(_lib.load().bb_set_drop_salt_ptr(self.salt_dev.data_ptr()), "bb_set_drop_salt_ptr")
         self.nstep = 0
         self.launches_per_replay = {}
