@@ -416,15 +416,21 @@ def run_ours(args, rank, world, local_rank):
     peaks = load_peaks()
     roof = None
     if rank == 0 or world == 1:
+        if reduce_grads is not None:
+            reduce_grads.enabled = False     # rank-local pass: the overlapped reducer must not issue collectives
         K.gemm_profile(True)
         try:
             for i in range(len(MIX)):
                 loss = model(resident[MIX[i]][0], MIX[i]).mean()     # un-wrapped module: no collective in this pass
                 loss.backward()
+                Bk.join_side()
+                Bk.PENDING_ADDS.clear()
                 model.zero_grad(set_to_none=True)
             torch.cuda.synchronize()
         finally:
             K.gemm_profile(False)
+            if reduce_grads is not None:
+                reduce_grads.enabled = True
         rec = [(2.0 * d[0] * d[1] * d[2] * d[3], ms_, d) for ms_, d in K.gemm_profile_records()]
         flops = sum(r[0] for r in rec)
         tms = sum(r[1] for r in rec)

@@ -40,6 +40,7 @@ class FlatGradAllReduce:
         self._arena_id = None
         self._done = 0
         self._launched = 0
+        self.enabled = True      # set False around rank-local forward/backward passes (no collective may be issued)
         if self.world > 1:
             from . import blocks
             blocks.AFTER_BLOCK_BWD = self._after_block
@@ -69,7 +70,7 @@ class FlatGradAllReduce:
         from . import blocks
         A = blocks.ARENA
         arena = A.buf
-        if self.world == 1 or not self._overlap_ok(arena):
+        if self.world == 1 or not self.enabled or not self._overlap_ok(arena):
             return
         if A.step_id != self._arena_id:                     # first block of a new step
             self._arena_id, self._done, self._launched = A.step_id, 0, 0
