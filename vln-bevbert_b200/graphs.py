@@ -97,8 +97,9 @@ class GraphedTrainStep:
             return self._eager(batch, task)
         if ent["graph"] is not None and self.reduce_grads is not None:
             # data-parallel: the graph holds forward + backward; the NCCL all-reduce and the optimizer run eagerly on the
-            # gradients the graph left in its (static) arena -- collectives stay out of the capture (a rank whose capture
-            # failed would otherwise execute them while the others only record them)
+            # gradients the graph left in its (static) arena.  Collectives stay out of the capture: a rank whose capture
+            # failed would execute them while the others only record them, and capturing the chunked reductions on the
+            # communication stream faulted on B200 (round 2, N=2: illegal address at the first replay) -- not pursued.
             self._next_salt()
             ent["graph"].replay()
             self._after_backward_eager(ent)
