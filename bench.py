@@ -418,6 +418,9 @@ def run_ours(args, rank, world, local_rank):
     if rank == 0 or world == 1:
         if reduce_grads is not None:
             reduce_grads.enabled = False     # rank-local pass: the overlapped reducer must not issue collectives
+        had_side = K.side_stream() is not None
+        if had_side:
+            enable_side_stream(False)        # serialise the GEMMs: a launch's span must not include a concurrent one
         K.gemm_profile(True)
         try:
             for i in range(len(MIX)):
@@ -429,6 +432,8 @@ def run_ours(args, rank, world, local_rank):
             torch.cuda.synchronize()
         finally:
             K.gemm_profile(False)
+            if had_side:
+                enable_side_stream(True)
             if reduce_grads is not None:
                 reduce_grads.enabled = True
         rec = [(2.0 * d[0] * d[1] * d[2] * d[3], ms_, d) for ms_, d in K.gemm_profile_records()]

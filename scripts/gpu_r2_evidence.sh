@@ -18,3 +18,11 @@ cd ../../..
 timeout 300 python scripts/bench_attn.py > gpurun_out/r02_bench_attn_final.log 2>&1; cat gpurun_out/r02_bench_attn_final.log
 timeout 300 python scripts/bench_hbm.py > gpurun_out/r02_bench_hbm_final.log 2>&1; cat gpurun_out/r02_bench_hbm_final.log
 ls -la gpurun_out/r02_*.ncu-rep
+# launch list of the final bench step (eager launches on one stream so that every kernel is listed and serial)
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 7400 -c 6700 --csv --log-file gpurun_out/r02_launches_final.csv \
+  python bench.py --steps 11 --warmup 11 --no-cpu-baseline --graphs 0 --side-stream 0 > gpurun_out/r02_launches_final.log 2>&1
+echo "== ncu launches rc=$?"; wc -l gpurun_out/r02_launches_final.csv
+# final bench line (graph replay, side stream), every GEMM shape to stderr
+BEVBERT_BENCH_VERBOSE=1 timeout 600 python bench.py --steps 22 --warmup 11 > gpurun_out/r02_bench_final.json 2> gpurun_out/r02_bench_final.err; echo "== bench rc=$?"
+python -c "
+import json; d=json.load(open('gpurun_out/r02_bench_final.json')); r=d['roofline']; print('value %.0f (%.2f ms) e2e %.0f (%.2f ms) launches %d gemm %.0f TF/s frac %.3f' % (d['value'], d['ms_per_step'], d['e2e']['value'], d['e2e']['ms_per_step'], d['gpu_launches'], r['achieved'], r['frac']))"
