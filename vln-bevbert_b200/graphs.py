@@ -8,9 +8,12 @@ What makes a step replayable here:
     stream -- bench.py's `dev_in` buffers); host-side index lists come from `ops.prepare_batch` (pinned tensors that
     the captured copy nodes re-read);
   * dropout seeds are kernel parameters frozen in the graph, so the per-step variation comes from the device-resident
-    salt every kernel XORs into its seed (`bb_set_drop_salt_ptr`): one 8-byte copy node at the head of the graph;
+    salt every kernel XORs into its seed (`bb_set_drop_salt_ptr`); the salt is advanced ON THE DEVICE (a 64-bit LCG
+    step, the first two nodes of the graph), so the mask sequence does not depend on how far the host runs ahead;
   * the optimizer's host half (per-parameter step counters, bias-corrected step sizes, lr schedule) is redone before
-    each replay by `optim.AdamW.advance`; the graph re-uploads the pinned launch table and runs the update kernels;
+    each replay by `optim.AdamW.advance`; the graph re-uploads the pinned launch table and runs the update kernels.
+    The host may not rewrite that table while a replay that still has to read it is queued: `AdamW.replayed` records
+    an event behind each replay and the next `advance` of the same table waits for it (kernels.MtTable);
   * parameter gradients are carved from the per-step arena inside the graph's memory pool: same addresses every replay.
 A graph is keyed by (task, identity and shapes of the batch tensors).  sem / masksem, whose per-item loss has a
 device-computed length, run in the model's `sync_free_mean` mode (mean over a device-side weight, same value and
@@ -25,16 +28,16 @@ from . import _lib
 EAGER_TASKS = ()      # every pre-training task is capturable (sem / masksem through the model's sync_free_mean mode)
 
 
-_SALT = {}      # device -> (pinned host word, device word): registered with the library once and never freed
+_SALT = {}      # device -> device word: registered with the library once and never freed
+_LCG_A, _LCG_C = 6364136223846793005, 1442695040888963407      # Knuth's MMIX multiplier / increment (mod 2^64)
 
 
 def _salt_buffers(dev):
     key = (dev.type, dev.index)
     if key not in _SALT:
-        host = torch.zeros(1, dtype=torch.int64).pin_memory()
         word = torch.zeros(1, dtype=torch.int64, device=dev)
         _lib.check(_lib.load().bb_set_drop_salt_ptr(word.data_ptr()), "bb_set_drop_salt_ptr")
-        _SALT[key] = (host, word)
+        _SALT[key] = word
     return _SALT[key]
 
 
@@ -45,9 +48,10 @@ class GraphedTrainStep:
         self.entries = {}
         self.pool = None
         dev = next(net.parameters()).device
-        self.salt_host, self.salt_dev = _salt_buffers(dev)
+        self.salt_dev = _salt_buffers(dev)
         _lib.check(_lib.load().bb_set_drop_salt_ptr(self.salt_dev.data_ptr()), "bb_set_drop_salt_ptr")
-        self.nstep = 0
+        # reproducible mask sequence: the salt restarts from the process seed for every training loop
+        self.salt_dev.fill_(blocks._mix64(torch.initial_seed() + 0x5A17) & 0x7FFFFFFFFFFFFFFF)
         self.launches_per_replay = {}
 
     @staticmethod
@@ -74,13 +78,12 @@ class GraphedTrainStep:
         return loss.detach()
 
     def _next_salt(self):
-        self.nstep += 1
-        self.salt_host[0] = blocks._mix64(self.nstep * 0x9E3779B97F4A7C15 + 12345) & 0x7FFFFFFFFFFFFFFF
+        """advance the device-resident dropout salt: enqueued eagerly, or recorded as the first nodes of a step graph"""
+        self.salt_dev.mul_(_LCG_A).add_(_LCG_C)
 
     def __call__(self, batch, task):
         if EAGER_TASKS and task.startswith(EAGER_TASKS):
             self._next_salt()
-            self.salt_dev.copy_(self.salt_host, non_blocking=True)
             return self._eager(batch, task)
         key = self._sig(batch, task)
         ent = self.entries.get(key)
@@ -89,18 +92,15 @@ class GraphedTrainStep:
         if ent["graph"] is None and ent["n"] < self.warmup:
             ent["n"] += 1
             self._next_salt()
-            self.salt_dev.copy_(self.salt_host, non_blocking=True)
             return self._eager(batch, task)
         if ent["graph"] is None and ent.get("failed"):
             self._next_salt()
-            self.salt_dev.copy_(self.salt_host, non_blocking=True)
             return self._eager(batch, task)
         if ent["graph"] is not None and self.reduce_grads is not None:
             # data-parallel: the graph holds forward + backward; the NCCL all-reduce and the optimizer run eagerly on the
             # gradients the graph left in its (static) arena.  Collectives stay out of the capture: a rank whose capture
             # failed would execute them while the others only record them, and capturing the chunked reductions on the
             # communication stream faulted on B200 (round 2, N=2: illegal address at the first replay) -- not pursued.
-            self._next_salt()
             ent["graph"].replay()
             self._after_backward_eager(ent)
             return ent["loss"]
@@ -116,12 +116,11 @@ class GraphedTrainStep:
                 for p in self.net.parameters():
                     p.grad = None
                 self._next_salt()
-                self.salt_dev.copy_(self.salt_host, non_blocking=True)
                 return self._eager(batch, task)
         else:
-            self._next_salt()
             self.opt.advance(ent["sig"])
             ent["graph"].replay()
+            self.opt.replayed(ent["sig"])
         return ent["loss"]
 
     def _after_backward_eager(self, ent):
@@ -142,13 +141,12 @@ class GraphedTrainStep:
         if self.pool is None:
             self.pool = torch.cuda.graph_pool_handle()
         g = torch.cuda.CUDAGraph()
-        self._next_salt()
         n0 = K.launch_count()
         dp = self.reduce_grads is not None
         hook, blocks.AFTER_BLOCK_BWD = blocks.AFTER_BLOCK_BWD, (None if dp else blocks.AFTER_BLOCK_BWD)
         try:
             with torch.cuda.graph(g, pool=self.pool):
-                self.salt_dev.copy_(self.salt_host, non_blocking=True)
+                self._next_salt()
                 loss = self.loss_fn(self._forward(batch, task))
                 loss.backward()
                 if dp:
@@ -172,6 +170,7 @@ class GraphedTrainStep:
             ent["sig"] = self.opt.last_sig
             # the capture only RECORDED the step (and advanced the optimizer's host counters for it): run it once
             g.replay()
+            self.opt.replayed(ent["sig"])
 
     def launches(self, batch, task):
         """kernels of libbevbert_b200.so inside the captured step of (batch, task), or None when it runs eagerly."""

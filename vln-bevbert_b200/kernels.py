@@ -590,10 +590,30 @@ class MtTable:
             c0 += (int(r[5]) + chunk - 1) // chunk
         self.chunks = c0
         self.dev = torch.empty(self.host.numel(), dtype=torch.uint8, device=device)
+        self.busy = None        # event behind the last enqueued copy that reads the pinned rows
         self.upload()
 
     def upload(self):
         self.dev.copy_(self.host, non_blocking=True)
+
+    # The pinned rows are read by an ASYNCHRONOUS copy (a plain one in eager steps, a memcpy node of the step graph in
+    # replay), while the host rewrites them for the next step that uses this table.  `mark_busy` is called after the
+    # work that reads the rows has been enqueued, `wait_idle` before the host touches them again: the host then never
+    # runs more than one step of THIS table ahead of the device (with two tasks alternating it waits on a step that
+    # finished long ago).  Neither is a graph node; both are skipped while the stream is capturing.
+    def mark_busy(self):
+        if self.dev.is_cuda and not capturing():
+            self.busy = torch.cuda.Event()
+            self.busy.record()
+
+    def wait_idle(self):
+        if self.busy is not None and not capturing():
+            self.busy.synchronize()
+            self.busy = None
+
+
+def capturing():
+    return torch.cuda.is_available() and torch.cuda.is_current_stream_capturing()
 
 
 def mt_cast_bf16(table: MtTable):

@@ -124,6 +124,7 @@ class AdamW:
     def _fill(self, tab, idx, sig, with_grads):
         """host half of a step: advance the per-parameter step counters and write step size / decay (and, outside
         graph replay, the gradient pointers) into the pinned launch table.  -> False when the table is out of date."""
+        tab.wait_idle()         # an upload of the previous step of this table may still be queued: do not race it
         rows = tab.np
         for r, i in enumerate(idx):
             gi, p = self.flat[i]
@@ -159,6 +160,7 @@ class AdamW:
         if not self._fill(tab, idx, sig, True):
             return self.step(grad_scale, set_to_none)
         tab.upload()
+        tab.mark_busy()
         b1, b2 = self.param_groups[0]["betas"]
         eps = self.param_groups[0]["eps"]
         clip = self.max_grad_norm is not None and self.max_grad_norm > 0
@@ -179,6 +181,11 @@ class AdamW:
         only the host half (step counters, bias-corrected step sizes, current lr) has to be redone before the replay."""
         tab, idx, _, _ = self._tables[sig]
         self._fill(tab, idx, sig, False)
+
+    def replayed(self, sig):
+        """call right after enqueuing a replay of a graph that holds step() of `sig`: its upload node reads the pinned
+        table until the replay has passed it (MtTable.mark_busy / wait_idle)."""
+        self._tables[sig][0].mark_busy()
 
     def total_grad_norm(self):
         """sqrt of the device-side sum of squares of the last clipped step (0-d tensor, no sync)."""
