@@ -69,11 +69,22 @@ class GraphedTrainStep:
                 mod.sync_free_mean = False
         return self.net(batch, task)
 
-    def _eager(self, batch, task):
-        loss = self.loss_fn(self._forward(batch, task))
-        loss.backward()
-        if self.reduce_grads is not None:
-            self.reduce_grads()
+    def _eager(self, batch, task, like_replay=False):
+        """one step with eager launches.  `like_replay` (data-parallel, this rank's capture failed): issue the same
+        collectives as the ranks that replay a graph -- ONE all-reduce of the whole arena after backward instead of the
+        chunked ones the backward hook would launch -- so that the ranks stay in step."""
+        rg = self.reduce_grads
+        chunked = getattr(rg, "enabled", None)
+        if like_replay and chunked is not None:
+            rg.enabled = False
+        try:
+            loss = self.loss_fn(self._forward(batch, task))
+            loss.backward()
+        finally:
+            if like_replay and chunked is not None:
+                rg.enabled = chunked
+        if rg is not None:
+            rg()
         self.opt.step()
         return loss.detach()
 
@@ -95,7 +106,7 @@ class GraphedTrainStep:
             return self._eager(batch, task)
         if ent["graph"] is None and ent.get("failed"):
             self._next_salt()
-            return self._eager(batch, task)
+            return self._eager(batch, task, like_replay=True)
         if ent["graph"] is not None and self.reduce_grads is not None:
             # data-parallel: the graph holds forward + backward; the NCCL all-reduce and the optimizer run eagerly on the
             # gradients the graph left in its (static) arena.  Collectives stay out of the capture: a rank whose capture
@@ -116,7 +127,7 @@ class GraphedTrainStep:
                 for p in self.net.parameters():
                     p.grad = None
                 self._next_salt()
-                return self._eager(batch, task)
+                return self._eager(batch, task, like_replay=True)
         else:
             self.opt.advance(ent["sig"])
             ent["graph"].replay()

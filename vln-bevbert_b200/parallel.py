@@ -29,7 +29,9 @@ class FlatGradAllReduce:
     contribution later in backward (the tied word-embedding / MLM-decoder matrix) keep both arena slices apart until
     the reductions are done (the average of the sum is the sum of the averages), see blocks.PENDING_ADDS.
     Gradients that live outside the arena (the first step of a task, the few small heads that run on torch autograd)
-    go through a second, small flat buffer.  Everything here is capturable in a CUDA graph (graphs.py)."""
+    go through a second, small flat buffer.  With graphs.GraphedTrainStep the graph holds forward + backward only and
+    this object is called once after the replay (one all-reduce of the whole arena): collectives stay out of the
+    capture (graphs.py explains why), so the chunked overlap is what the EAGER loop gets."""
 
     def __init__(self, params, world_size=None, chunks=3):
         self.params = [p for p in params if p.requires_grad]
