@@ -1,8 +1,16 @@
-// Attention core on tcgen05 tensor cores, fed by TMA, for head dim 64 and >= 64 keys (forward).
+// Attention core on tcgen05 tensor cores, fed by TMA, for head dim 64 and >= 64 keys.
 //
 //   O = dropout(softmax(alpha Q K^T + kmask)) V        per (sample, head), scores / probabilities never leave the SM
 //
-// One CTA owns 128 queries of one (sample, head):
+// Three kernels live here (dispatch at the bottom: launch_fwd / launch_bwd, called from attn_flash.cu):
+//   attn_tc_fwd2_kernel    the DEFAULT forward: K / V stream in 64-key blocks, 256 TMEM columns, two CTAs per SM
+//                          (described at its definition, "forward, streaming");
+//   attn_tc_bwd_kernel<M>  backward, dQ pass (M = 0) and dK / dV pass (M = 1) (described at its definition);
+//   attn_tc_fwd_kernel     the first-generation forward described next; serves rows longer than 4096 keys (the streaming
+//                          kernel stages the whole key mask in shared memory) and BB_ATTN_FWD=1 (A/B measurements: 146 us
+//                          against 89 us at 441 x 441; the reference point of profiles/r02_attention.md).
+//
+// First-generation forward.  One CTA owns 128 queries of one (sample, head):
 //   warp 0 (one elected lane)  TMA producer + MMA issuer:
 //        Q (128 x 64) and all K / V rows of a "super-block" of up to 448 keys arrive by cp.async.bulk.tensor (128-byte
 //        swizzle, zero fill past the last row); S = Q K^T is one or two tcgen05.mma groups (M 128, N <= 256, 4 k-steps)
@@ -15,7 +23,6 @@
 //        saved for backward.
 // The whole key range of a super-block is in TMEM at once (441 BEV cells -> 448 columns), so there is no online-softmax
 // rescaling of O; longer rows (RxR, 512 keys) run as several super-blocks merged in registers.
-//
 // TMEM: 512 columns = O (64) + S (448).  Shared memory: Q 16 KB + K 56 KB + V 56 KB + P 2 x 16 KB.
 //
 // Reference semantics: BertSelfAttention / BertOutAttention (vilmodel.py:103-154, 325-363); same dropout function and
