@@ -394,7 +394,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
 
 // ================================================================================================ forward, streaming
 // Second-generation forward (the default): K / V stream through shared memory in 64-key blocks, S is double-buffered in
-// TMEM (2 x 64 columns + 64 for O = 256 allocated columns) and the CTA is small (6 warps, 96 KB of shared memory), so
+// TMEM (2 x 64 columns + 64 for O = 256 allocated columns) and the CTA is small (10 warps, 98 KB of shared memory), so
 // TWO CTAs share an SM and each one overlaps its own tensor-pipe work with its element-wise work: profiling of the
 // first version (whole key range in TMEM, one CTA per SM) showed 28 % issue utilisation -- the warps mostly waited on
 // mbarriers (loads, MMAs) with nothing else resident to run.
