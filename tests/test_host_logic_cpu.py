@@ -97,3 +97,27 @@ def test_direct_param_grads_equal_autograd_accumulation(emu):
     assert set(grads[False]) == set(grads[True])
     for n, g in grads[False].items():
         assert torch.allclose(g, grads[True][n], rtol=1e-6, atol=1e-7), n
+
+
+def test_forward_sees_weights_updated_behind_the_version_counter(emu):
+    """Optimizers write `p.data` (torch._fused_adamw_, the reference's `p.data.add_`, optim/adamw.py:103-110) without
+    bumping `p._version`, so the operand shadows kept by blocks.WeightCache cannot rely on versions (round-1 advisor
+    finding): a training forward after such an update must use the new weights, here against the oracle on CPU."""
+    cfg, scfg = small_config(), small_synth()
+    model = synth.det_init_(GlocalTextPathCMTPreTraining(cfg), seed=3).train()
+    b = synth.make_batch(scfg, seed=7, task="mlm")
+    out0 = model(synth.clone_batch(b), "mlm").detach()
+    touched = [model.bert.lang_encoder.layer[0].attention.self.query.weight,        # stacked Q|K|V shadow
+               model.bert.lang_encoder.layer[0].intermediate.dense.weight,          # plain shadow
+               model.bert.lang_encoder.layer[0].output.LayerNorm.weight,            # fp32 vector entry
+               model.bert.lang_encoder.layer[0].attention.self.key.bias]            # packed bias
+    versions = [p._version for p in touched]
+    with torch.no_grad():
+        for p in touched:
+            p.data.mul_(1.25).add_(0.01)
+    assert [p._version for p in touched] == versions      # the premise: nothing for a version check to see
+    out1 = model(synth.clone_batch(b), "mlm").detach()
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    ref = R.forward(sd, synth.clone_batch(b), "mlm", R.OracleConfig(cfg)).detach()
+    assert not torch.allclose(out1, out0, rtol=1e-3, atol=1e-4)
+    assert torch.allclose(out1, ref, rtol=1e-4, atol=1e-5), float((out1 - ref).abs().max())

@@ -602,17 +602,17 @@ class MtTable:
     # runs more than one step of THIS table ahead of the device (with two tasks alternating it waits on a step that
     # finished long ago).  Neither is a graph node; both are skipped while the stream is capturing.
     def mark_busy(self):
-        if self.dev.is_cuda and not capturing():
+        if self.dev.is_cuda and not _capturing():
             self.busy = torch.cuda.Event()
             self.busy.record()
 
     def wait_idle(self):
-        if self.busy is not None and not capturing():
+        if self.busy is not None and not _capturing():
             self.busy.synchronize()
             self.busy = None
 
 
-def capturing():
+def _capturing():
     return torch.cuda.is_available() and torch.cuda.is_current_stream_capturing()
 
 
