@@ -17,7 +17,8 @@ namespace bb {
 
 // ---------------------------------------------------------------------------------------------
 // One thread per point. All arithmetic uses explicit round-to-nearest single operations (no FMA
-// contraction) in a fixed order so that the CPU oracle (oracle/bev_oracle.py) reproduces every bit.
+// contraction) in a fixed order so that the CPU oracle (oracle/bevbert_ref.py: lift_points, cell_index) reproduces
+// every bit.
 // ---------------------------------------------------------------------------------------------
 __global__ void lift_index_kernel(const float* __restrict__ depths, const float* __restrict__ T_c2w,
                                   const float* __restrict__ S_w2c, const float* __restrict__ T_w2c, int B, int V, int Hf,

@@ -124,6 +124,16 @@ static int lin_bwd_dx(const void* dy, const void* w, void* out, int64_t M, int N
   g.add_in = add_in; g.split_k = 1; g.drop_seed = seed; g.drop_thresh = th; g.drop_scale = sc;
   return bb_gemm_bf16(&g, stream);
 }
+static int num_sms() {     // split-K factor of the weight-gradient products: fill the machine this library runs on
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+  }
+  return n;
+}
 // dW (N, Kd) += dy^T x   (fp32, zeroed by the caller)
 static int lin_bwd_dw(const void* dy, const void* x, float* out, int64_t M, int N, int Kd, void* stream) {
   bb_gemm_args g;
@@ -133,7 +143,7 @@ static int lin_bwd_dw(const void* dy, const void* x, float* out, int64_t M, int 
   if (Kd <= bn) bn = 0;
   const int tiles = bn ? m_t * ((Kd + bn - 1) / bn) : m_t;
   const int64_t kb = (M + 63) / 64;
-  int64_t split = (148 + tiles / 2) / (tiles > 0 ? tiles : 1);
+  int64_t split = (num_sms() + tiles / 2) / (tiles > 0 ? tiles : 1);
   const int64_t cap = kb >= 8 ? kb / 8 : 1;
   if (split > cap) split = cap;
   if (split < 1) split = 1;
