@@ -121,3 +121,27 @@ def test_forward_sees_weights_updated_behind_the_version_counter(emu):
     ref = R.forward(sd, synth.clone_batch(b), "mlm", R.OracleConfig(cfg)).detach()
     assert not torch.allclose(out1, out0, rtol=1e-3, atol=1e-4)
     assert torch.allclose(out1, ref, rtol=1e-4, atol=1e-5), float((out1 - ref).abs().max())
+
+
+def test_edge_cases_longest_trajectory_and_empty_bev(emu):
+    """SURVEY section 4 property cases on the host logic: the longest trajectory the loaders produce (TRAIN_MAX_STEP + 1 = 21
+    panoramas, dataset.py:185-187), and a batch whose depth maps are all zero (every point dropped: an empty BEV, all
+    cells `ob_mask` False, `bev_utils.py:393-430`)."""
+    _run("sap", small_config(), small_synth(pano_min=21, pano_max=21))
+    for task in ("sap", "mlm"):
+        _run(task, small_config(), small_synth(depth_zero_frac=1.0))
+
+
+def test_reverie_batch_contains_viewpoints_without_objects(emu):
+    """zero-object viewpoints (and a last viewpoint without objects -> label -100, pretrain_cmt.py:380-389) are part of the
+    REVERIE parity cases above, not an accident of the seed"""
+    scfg = small_synth(obj_feat_size=768, obj_max=5, obj_prob_size=100, batch_size=4)
+    cfg = small_config(obj_feat_size=768, obj_prob_size=100, pretrain_tasks=["mlm", "mrc", "sap", "og"])
+    for seed in range(7, 40):
+        b = synth.make_batch(scfg, seed=seed, task="og")
+        if int((b["traj_vp_obj_lens"] == 0).sum()) > 0 and int((b["obj_labels"] == -100).sum()) > 0 \
+                and int((b["obj_labels"] >= 0).sum()) > 0:
+            break
+    else:
+        raise AssertionError("no seed with an object-free last viewpoint")
+    _run("og", cfg, scfg, seed=seed)

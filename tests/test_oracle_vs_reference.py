@@ -34,6 +34,22 @@ def test_restatement_equals_reference(task):
     assert torch.allclose(got, want, rtol=1e-5, atol=1e-6), float((got - want).abs().max())
 
 
+@pytest.mark.parametrize("case", ["longest_trajectory", "empty_bev"])
+def test_restatement_equals_reference_on_edge_cases(case):
+    """SURVEY section 4 property cases, pinned on the unmodified reference: 21 panoramas per trajectory (TRAIN_MAX_STEP + 1,
+    dataset.py:185-187) and depth maps that are all zero (every point dropped, all BEV cells empty)."""
+    cfg = small_config()
+    scfg = small_synth(pano_min=21, pano_max=21) if case == "longest_trajectory" else small_synth(depth_zero_frac=1.0)
+    sd = {k: v.detach().clone() for k, v in synth.det_init_(GlocalTextPathCMTPreTraining(cfg), seed=5).state_dict().items()}
+    ref = _ref_model(cfg, sd)
+    for task in ("sap", "mlm"):
+        b = synth.make_batch(scfg, seed=23, task=task)
+        want = ref(synth.clone_batch(b), task, compute_loss=True)
+        got = R.forward(sd, synth.clone_batch(b), task, R.OracleConfig(cfg))
+        assert torch.isfinite(want).all()
+        assert torch.allclose(got, want, rtol=1e-5, atol=1e-6), (task, float((got - want).abs().max()))
+
+
 def test_bev_projection_matches_reference_bit_for_bit():
     """lift + project_bev of the reference (torch bmm / matmul + scatter_mean stub) vs the fixed-order oracle:
     cell indices, pooled features, semantic maps and masks."""
