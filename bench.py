@@ -464,10 +464,12 @@ def run_ours(args, rank, world, local_rank):
                 "peak_burst": peaks["bf16_tflops"],
                 "frac_of_burst_peak": (achieved / peaks["bf16_tflops"]) if peaks["bf16_tflops"] else None,
                 "traffic": None, "gemm_ms_per_step": tms / len(MIX), "gemm_flops_per_step": flops / len(MIX),
-                "model_flops_frac": value / world * FLOPS_PER_SAMPLE_FWD_BWD / 1e12 / peak,
+                # the two model-level figures use SURVEY 8(d)'s flop counts of the R2R configuration
+                "model_flops_frac": (value / world * FLOPS_PER_SAMPLE_FWD_BWD / 1e12 / peak) if WORKLOAD == "r2r" else None,
                 # north_star "achieved fraction of the attention-GEMM roofline": attention-GEMM flops the job retires
                 # per second (mix-weighted, fwd + bwd) over the bf16 peak
-                "attn_gemm_roofline_frac": value / world * ATTN_GEMM_FLOPS_MIX_FWD_BWD / 1e12 / peak}
+                "attn_gemm_roofline_frac": (value / world * ATTN_GEMM_FLOPS_MIX_FWD_BWD / 1e12 / peak)
+                if WORKLOAD == "r2r" else None}
 
     # ------------------------------------------------------------------ CPU baseline (rank 0, N == 1, bounded sample)
     cpu = None
