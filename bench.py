@@ -267,6 +267,10 @@ def run_ours(args, rank, world, local_rank):
         opt = AdamW(build_param_groups(model, 0.01), lr=5e-5, betas=(0.9, 0.98), eps=1e-6, max_grad_norm=5.0,
                     runtime=model.rt)
     Bs = args.batch
+    if args.strong:          # north_star's strong-scaling figure: the 32-sample global batch is split over the ranks
+        if args.batch % world:
+            raise SystemExit("--strong: --batch %d is not divisible by %d ranks" % (args.batch, world))
+        Bs = args.batch // world
     scfg = synth_config(Bs)
     from bevbert_b200.model.ops import prepare_batch
     # prepare_batch = collate-time host index building (DataLoader-worker work in the reference's pipeline)
@@ -500,7 +504,7 @@ def run_ours(args, rank, world, local_rank):
     if rank == 0:
         out = {
             "metric": "pretrain_samples_per_s", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if args.strong else "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": "%s; batch %d/GPU; lift-splat + fwd + bwd%s + grad-norm clip + AdamW (reference update "
                                    "rule); tasks cycle %s; dropout 0.1" % (
@@ -537,6 +541,8 @@ def main():
     ap.add_argument("--wire", choices=("bf16", "fp32"), default="bf16",
                     help="host dtype of the large feature tensors in the end-to-end leg")
     ap.add_argument("--ddp", action="store_true", help="wrap with torch DDP instead of the flat gradient all-reduce")
+    ap.add_argument("--strong", action="store_true",
+                    help="strong scaling: --batch is the GLOBAL batch, split over the ranks (default: weak, --batch per GPU)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     global WORKLOAD, MIX
